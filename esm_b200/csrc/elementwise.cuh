@@ -1,0 +1,152 @@
+// esm_b200 — HBM-bound row kernels around the tensor-core GEMMs (sm_100a).
+//
+//   layernorm_rows    esm/modules.py:68-81,124,137 and esm/model/esm2.py:123 (torch.nn.LayerNorm, eps 1e-5, affine),
+//                     one warp per row, the row held in registers (single HBM read), fp16 or fp32 output
+//   embed_tokens      esm/model/esm2.py:84-95 (embedding gather, <mask> zeroing, token-dropout rescale
+//                     0.88/(1-mask_ratio), pad zeroing)
+//   key_bits          esm/model/esm2.py:82 + multihead_attention.py:368-374 (key padding mask) packed to 1 bit/key
+//   convert_f32_f16   weight packing (fp32 nn.Linear weights -> fp16 MMA operands)
+#pragma once
+
+#include "common.cuh"
+
+namespace esmb200 {
+
+// Each lane owns float4 chunks lane, lane+32, ... of the row. MAXV bounds E <= MAXV*128.
+template <int MAXV, bool OUT_HALF>
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      void* __restrict__ out, int M, int E, float eps) {
+  const int warps_per_block = blockDim.x / 32;
+  const int row = blockIdx.x * warps_per_block + threadIdx.x / 32;
+  if (row >= M) return;
+  const int lane = threadIdx.x % 32;
+  const int nvec = E / 4;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if constexpr (OUT_HALF) {
+        uint2 h;
+        h.x = pack_half2(o.x, o.y);
+        h.y = pack_half2(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (size_t)row * E)[idx] = h;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * E)[idx] = o;
+      }
+    }
+  }
+}
+
+template <bool OUT_HALF>
+inline cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int E,
+                                    float eps, cudaStream_t stream) {
+  if (E % 4 != 0 || E > 40 * 128) return cudaErrorInvalidValue;
+  const int wpb = 8;
+  const int grid = (M + wpb - 1) / wpb;
+  if (grid == 0) return cudaSuccess;
+  if (E <= 4 * 128) layernorm_rows_kernel<4, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
+  else if (E <= 10 * 128) layernorm_rows_kernel<10, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
+  else if (E <= 20 * 128) layernorm_rows_kernel<20, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
+  else layernorm_rows_kernel<40, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
+  return cudaGetLastError();
+}
+
+// One block per sequence: counts <mask>/<pad>, then writes the scaled embedding rows.
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ table, float* __restrict__ x, int T,
+                    int E, int padding_idx, int mask_idx, int token_dropout) {
+  const int b = blockIdx.x;
+  const int64_t* tok = tokens + (size_t)b * T;
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int n_mask = 0, n_pad = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int64_t v = tok[t];
+    n_mask += (v == mask_idx);
+    n_pad += (v == padding_idx);
+  }
+  n_mask = (int)warp_sum((float)n_mask);
+  n_pad = (int)warp_sum((float)n_pad);
+  if (threadIdx.x % 32 == 0) {
+    atomicAdd(&s_cnt[0], n_mask);
+    atomicAdd(&s_cnt[1], n_pad);
+  }
+  __syncthreads();
+  // esm2.py:86-92: x.masked_fill_(mask, 0); x = x * (1 - 0.15*0.8) / (1 - n_mask / src_length)
+  // (python evaluates 1 - 0.15*0.8 in double, the tensor ops run in fp32: multiply first, then divide)
+  const float keep = (float)(1.0 - 0.15 * 0.8);
+  const float denom = 1.0f - (float)s_cnt[0] / (float)(T - s_cnt[1]);
+  const int nvec = E / 4;
+  for (int i = threadIdx.x; i < T * nvec; i += blockDim.x) {
+    const int t = i / nvec, c = i % nvec;
+    const int64_t v = tok[t];
+    float4 e = __ldg(reinterpret_cast<const float4*>(table + (size_t)v * E) + c);
+    if (token_dropout) {
+      if (v == mask_idx) e = make_float4(0.f, 0.f, 0.f, 0.f);
+      e.x = (e.x * keep) / denom;
+      e.y = (e.y * keep) / denom;
+      e.z = (e.z * keep) / denom;
+      e.w = (e.w * keep) / denom;
+    }
+    if (v == padding_idx) e = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(x + ((size_t)b * T + t) * E)[c] = e;
+  }
+}
+
+// keybits[b, w] bit i = key 32w+i attendable; kvlen[b] = 1 + last attendable key. One warp per sequence.
+__global__ void key_bits_kernel(const uint8_t* __restrict__ pad_mask, uint32_t* __restrict__ keybits,
+                                int* __restrict__ kvlen, int B, int T, int words) {
+  const int b = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (b >= B) return;
+  const int lane = threadIdx.x % 32;
+  int last = 0;
+  for (int w = 0; w < words; ++w) {
+    const int key = w * 32 + lane;
+    bool ok = key < T;
+    if (ok && pad_mask) ok = pad_mask[(size_t)b * T + key] == 0;
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) keybits[(size_t)b * words + w] = bits;
+    if (bits) last = w * 32 + (32 - __clz(bits));
+  }
+  if (lane == 0) kvlen[b] = last;
+}
+
+__global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+}
+
+}  // namespace esmb200

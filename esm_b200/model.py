@@ -1,0 +1,342 @@
+"""Host-side mirror of the reference's ESM-2 interface, dispatching the transformer-layer path to libesmb200.so.
+
+Mirrors (same names, argument meaning, state-dict keys and result dict):
+    esm.modules.TransformerLayer.forward       /root/reference/esm/modules.py:120-142
+    esm.model.esm2.ESM2.__init__ / forward     /root/reference/esm/model/esm2.py:15-144
+PyTorch owns parameters, activations and the workspace (torch tensors) and provides the CUDA stream; every layer's
+compute goes through the C ABI in include/esmb200.h.  There is no CPU or eager fallback: on a non-CUDA tensor, or
+when libesmb200.so is missing, the forward raises.
+
+Documented deviations from the reference:
+  * `TransformerLayer.forward` returns `attn=None` unless `need_head_weights=True` (the reference always computes a
+    head-averaged (B,T,T) map that ESM2.forward discards, modules.py:130 / esm2.py:112-121).
+  * MMA operands are fp16 (fp32 accumulate, fp32 residual stream / LayerNorm / softmax); tolerance in DESIGN.md.
+  * head_dim must be 64.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .alphabet import Alphabet
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class RotaryEmbedding(nn.Module):
+    """Holds the `inv_freq` buffer under the reference's key (rotary_embedding.py:37-41); tables are built by
+    ESM2._rope_tables with the same torch ops as rotary_embedding.py:47-61."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer("inv_freq", inv_freq)
+
+
+class MultiheadAttention(nn.Module):
+    """Parameter container with the reference's names (multihead_attention.py:109-113,130-132)."""
+
+    def __init__(self, embed_dim: int, num_heads: int):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.head_dim = embed_dim // num_heads
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.rot_emb = RotaryEmbedding(self.head_dim)
+
+
+def rope_tables(inv_freq: torch.Tensor, seq_len: int):
+    """cos/sin [T, d/2] fp32 — rotary_embedding.py:53-59 (the reference's table is this one duplicated on the last dim)."""
+    t = torch.arange(seq_len, device=inv_freq.device).type_as(inv_freq)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    return freqs.cos().contiguous(), freqs.sin().contiguous()
+
+
+class TransformerLayer(nn.Module):
+    """Pre-LN transformer block of ESM-2 (modules.py:84-142) executed by libesmb200.so."""
+
+    def __init__(self, embed_dim: int, ffn_embed_dim: int, attention_heads: int):
+        super().__init__()
+        if embed_dim != 64 * attention_heads:
+            raise ValueError("esm_b200 supports head_dim == 64 only (embed_dim == 64 * attention_heads)")
+        self.embed_dim = embed_dim
+        self.ffn_embed_dim = ffn_embed_dim
+        self.attention_heads = attention_heads
+        self.self_attn = MultiheadAttention(embed_dim, attention_heads)
+        self.self_attn_layer_norm = nn.LayerNorm(embed_dim)
+        self.fc1 = nn.Linear(embed_dim, ffn_embed_dim)
+        self.fc2 = nn.Linear(ffn_embed_dim, embed_dim)
+        self.final_layer_norm = nn.LayerNorm(embed_dim)
+        self._handle = None
+        self._handle_key = None
+
+    # ---- C-ABI handle management -------------------------------------------------------------------------------
+    def _params(self) -> List[torch.Tensor]:
+        a = self.self_attn
+        return [self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias, a.q_proj.weight, a.q_proj.bias,
+                a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias,
+                self.final_layer_norm.weight, self.final_layer_norm.bias, self.fc1.weight, self.fc1.bias,
+                self.fc2.weight, self.fc2.bias]
+
+    def handle(self):
+        """esmb200_layer* for the current parameters; re-packed when a parameter is replaced or modified in place."""
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        self.release()
+        for p in ps:
+            if not p.is_cuda:
+                raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: move the model with .cuda(); "
+                                        "there is no CPU fallback")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.Esmb200Error("esm_b200 expects contiguous fp32 master parameters")
+        lib = _lib.load()
+        w = _lib.LayerWeights()
+        w.embed_dim, w.num_heads, w.ffn_dim = self.embed_dim, self.attention_heads, self.ffn_embed_dim
+        w.ln_eps = self.self_attn_layer_norm.eps
+        names = [f[0] for f in _lib.LayerWeights._fields_[4:]]
+        for n, p in zip(names, ps):
+            setattr(w, n, p.data_ptr())
+        out = ctypes.c_void_p()
+        with torch.cuda.device(ps[0].device):
+            _lib.check(lib.esmb200_layer_create(ctypes.byref(w), _stream(), ctypes.byref(out)))
+        self._handle, self._handle_key = out, key
+        return out
+
+    def release(self):
+        if self._handle is not None:
+            _lib.load().esmb200_layer_destroy(self._handle)
+            self._handle, self._handle_key = None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # ---- reference-facing forward ------------------------------------------------------------------------------
+    def forward(self, x, self_attn_mask=None, self_attn_padding_mask=None, need_head_weights=False):
+        """x: (T, B, E) like the reference (modules.py:120-122). Returns (x (T,B,E), attn (H,B,T,T) or None)."""
+        if self_attn_mask is not None:
+            raise NotImplementedError("ESM-2 never passes self_attn_mask (esm2.py:112-116)")
+        T, B, E = x.shape
+        xb = x.transpose(0, 1).contiguous().float()  # (B,T,E) batch-major copy, updated in place
+        cos, sin = rope_tables(self.self_attn.rot_emb.inv_freq, T)
+        attn = run_stack([self], xb, self_attn_padding_mask, cos, sin, None, [0] if need_head_weights else [])
+        out = xb.transpose(0, 1).to(x.dtype)
+        if need_head_weights:
+            return out, attn[0].transpose(0, 1)  # (B,H,T,T) -> (H,B,T,T), multihead_attention.py:398-400
+        return out, None
+
+
+_workspaces: Dict[torch.device, torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        _workspaces.pop(device, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask: Optional[torch.Tensor],
+              rope_cos: torch.Tensor, rope_sin: torch.Tensor, repr_out: Optional[Dict[int, torch.Tensor]],
+              attn_layers: Sequence[int]):
+    """esmb200_stack_forward on x fp32 (B,T,E) in place. repr_out: {layer index (0-based): (B,T,E) tensor to fill}.
+    Returns {layer index: (B,H,T,T) fp32} for the indices in attn_layers."""
+    if not x.is_cuda:
+        raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    lib = _lib.load()
+    B, T, E = x.shape
+    n = len(layers)
+    Fdim, H = layers[0].ffn_embed_dim, layers[0].attention_heads
+    with torch.cuda.device(x.device):
+        handles = (ctypes.c_void_p * n)(*[l.handle() for l in layers])
+        nbytes = lib.esmb200_workspace_bytes(E, Fdim, B, T)
+        ws = _workspace(nbytes, x.device)
+        mask = None
+        if padding_mask is not None:
+            mask = padding_mask.to(device=x.device, dtype=torch.uint8).contiguous()
+            assert mask.shape == (B, T)
+        reprs = (ctypes.c_void_p * n)()
+        keep = []
+        if repr_out:
+            for i, t in repr_out.items():
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape
+                reprs[i] = t.data_ptr()
+        attns = (ctypes.c_void_p * n)()
+        attn_t = {}
+        for i in attn_layers:
+            a = torch.empty((B, H, T, T), dtype=torch.float32, device=x.device)
+            attn_t[i] = a
+            attns[i] = a.data_ptr()
+        keep.append(mask)
+        _lib.check(lib.esmb200_stack_forward(handles, n, _ptr(x), _ptr(mask), B, T, _ptr(rope_cos), _ptr(rope_sin),
+                                             reprs if repr_out else None, attns if attn_layers else None,
+                                             _ptr(ws), ws.numel(), _stream()))
+    return attn_t
+
+
+def gelu(x):
+    """modules.py:17-24"""
+    return x * 0.5 * (1.0 + torch.erf(x / 1.4142135623730951))
+
+
+class RobertaLMHead(nn.Module):
+    """modules.py:298-314 — kept in PyTorch fp32 (0.23 % of the FLOPs; SURVEY §8f #2 lists it as a next row)."""
+
+    def __init__(self, embed_dim, output_dim, weight):
+        super().__init__()
+        self.dense = nn.Linear(embed_dim, embed_dim)
+        self.layer_norm = nn.LayerNorm(embed_dim)
+        self.weight = weight
+        self.bias = nn.Parameter(torch.zeros(output_dim))
+
+    def forward(self, features):
+        x = self.dense(features)
+        x = gelu(x)
+        x = self.layer_norm(x)
+        return F.linear(x, self.weight) + self.bias
+
+
+class ContactPredictionHead(nn.Module):
+    """modules.py:317-357 (symmetrize :27-29, apc :32-41) — PyTorch; SURVEY §8f #1 lists it as a next row."""
+
+    def __init__(self, in_features: int, prepend_bos: bool, append_eos: bool, bias=True, eos_idx: Optional[int] = None):
+        super().__init__()
+        self.in_features = in_features
+        self.prepend_bos = prepend_bos
+        self.append_eos = append_eos
+        if append_eos and eos_idx is None:
+            raise ValueError("Using an alphabet with eos token, but no eos token was passed in.")
+        self.eos_idx = eos_idx
+        self.regression = nn.Linear(in_features, 1, bias)
+        self.activation = nn.Sigmoid()
+
+    def forward(self, tokens, attentions):
+        if self.append_eos:
+            eos_mask = tokens.ne(self.eos_idx).to(attentions)
+            eos_mask = eos_mask.unsqueeze(1) * eos_mask.unsqueeze(2)
+            attentions = attentions * eos_mask[:, None, None, :, :]
+            attentions = attentions[..., :-1, :-1]
+        if self.prepend_bos:
+            attentions = attentions[..., 1:, 1:]
+        batch_size, layers, heads, seqlen, _ = attentions.size()
+        attentions = attentions.reshape(batch_size, layers * heads, seqlen, seqlen)
+        attentions = attentions.to(self.regression.weight.device)
+        x = attentions + attentions.transpose(-1, -2)
+        a1 = x.sum(-1, keepdims=True)
+        a2 = x.sum(-2, keepdims=True)
+        a12 = x.sum((-1, -2), keepdims=True)
+        avg = a1 * a2
+        avg.div_(a12)
+        x = (x - avg).permute(0, 2, 3, 1)
+        return self.activation(self.regression(x).squeeze(3))
+
+
+class ESM2(nn.Module):
+    """Drop-in for esm.model.esm2.ESM2 (esm2.py:14-147): same constructor, same state-dict keys (so
+    `load_state_dict(reference_model.state_dict())` and the esm2_t*.pt checkpoints load), same forward contract."""
+
+    def __init__(self, num_layers: int = 33, embed_dim: int = 1280, attention_heads: int = 20,
+                 alphabet: Union[Alphabet, str] = "ESM-1b", token_dropout: bool = True):
+        super().__init__()
+        self.num_layers = num_layers
+        self.embed_dim = embed_dim
+        self.attention_heads = attention_heads
+        if isinstance(alphabet, str):
+            alphabet = Alphabet.from_architecture(alphabet)
+        self.alphabet = alphabet
+        self.alphabet_size = len(alphabet)
+        self.padding_idx = alphabet.padding_idx
+        self.mask_idx = alphabet.mask_idx
+        self.cls_idx = alphabet.cls_idx
+        self.eos_idx = alphabet.eos_idx
+        self.prepend_bos = alphabet.prepend_bos
+        self.append_eos = alphabet.append_eos
+        self.token_dropout = token_dropout
+        self.embed_scale = 1
+        self.embed_tokens = nn.Embedding(self.alphabet_size, embed_dim, padding_idx=self.padding_idx)
+        self.layers = nn.ModuleList(
+            [TransformerLayer(embed_dim, 4 * embed_dim, attention_heads) for _ in range(num_layers)])
+        self.contact_head = ContactPredictionHead(num_layers * attention_heads, self.prepend_bos, self.append_eos,
+                                                  eos_idx=self.eos_idx)
+        self.emb_layer_norm_after = nn.LayerNorm(embed_dim)
+        self.lm_head = RobertaLMHead(embed_dim, self.alphabet_size, self.embed_tokens.weight)
+        self._rope_cache = None
+
+    def _rope_tables(self, T: int):
+        inv = self.layers[0].self_attn.rot_emb.inv_freq
+        key = (T, inv.device, inv.data_ptr())
+        if self._rope_cache is None or self._rope_cache[0] != key:
+            self._rope_cache = (key,) + rope_tables(inv, T)
+        return self._rope_cache[1], self._rope_cache[2]
+
+    @torch.no_grad()
+    def forward(self, tokens, repr_layers=[], need_head_weights=False, return_contacts=False):
+        if return_contacts:
+            need_head_weights = True
+        assert tokens.ndim == 2
+        if not tokens.is_cuda:
+            raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: pass tokens.cuda(); no CPU fallback")
+        lib = _lib.load()
+        tokens = tokens.contiguous()
+        B, T = tokens.shape
+        E, N = self.embed_dim, self.num_layers
+        padding_mask = tokens.eq(self.padding_idx)  # esm2.py:82
+        repr_layers = set(repr_layers)
+        hidden: Dict[int, torch.Tensor] = {}
+
+        with torch.cuda.device(tokens.device):
+            # esm2.py:84-95 embedding prologue
+            x = torch.empty((B, T, E), dtype=torch.float32, device=tokens.device)
+            _lib.check(lib.esmb200_embed_tokens(_ptr(tokens), _ptr(self.embed_tokens.weight), _ptr(x), B, T, E,
+                                                self.padding_idx, self.mask_idx, int(self.token_dropout), _stream()))
+            if 0 in repr_layers:
+                hidden[0] = x.clone()
+            mask = padding_mask if bool(padding_mask.any()) else None  # esm2.py:108-109
+            # esm2.py:111-121 layer loop (intermediate representations are copied out by the library)
+            repr_out = {i - 1: torch.empty_like(x) for i in repr_layers if 0 < i < N}
+            cos, sin = self._rope_tables(T)
+            attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out, list(range(N)) if need_head_weights else [])
+            for i, t in repr_out.items():
+                hidden[i + 1] = t
+            # esm2.py:123-128 final LayerNorm; the last representation is post-LN
+            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(self.emb_layer_norm_after.weight),
+                                             _ptr(self.emb_layer_norm_after.bias), _ptr(x), B * T, E,
+                                             self.emb_layer_norm_after.eps, _stream()))
+        if N in repr_layers:
+            hidden[N] = x
+        logits = self.lm_head(x)
+        result = {"logits": logits, "representations": hidden}
+        if need_head_weights:
+            attentions = torch.stack([attn_t[i] for i in range(N)], 1)  # B x L x H x T x T (esm2.py:134)
+            if mask is not None:
+                am = 1 - mask.type_as(attentions)
+                am = am.unsqueeze(1) * am.unsqueeze(2)
+                attentions = attentions * am[:, None, None, :, :]
+            result["attentions"] = attentions
+            if return_contacts:
+                result["contacts"] = self.contact_head(tokens, attentions)
+        return result
+
+    def predict_contacts(self, tokens):
+        return self(tokens, return_contacts=True)["contacts"]

@@ -1,0 +1,133 @@
+/* esmb200.h — C ABI of the B200-native ESM-2 transformer-layer forward path (libesmb200.so).
+ *
+ * The reference (facebookresearch/esm, fair-esm 2.0.1) is pure Python and has no FFI for this path; the seam this
+ * library sits behind is the Python method
+ *     esm.modules.TransformerLayer.forward(x, self_attn_mask, self_attn_padding_mask, need_head_weights)
+ *                                                      /root/reference/esm/modules.py:120-142
+ * called from ESM2.forward's layer loop                 /root/reference/esm/model/esm2.py:111-121
+ * Each entry point below names the reference code it replaces. The reference-side binding (a ctypes stub) is shown in
+ * INTEGRATION.md; esm_b200/_lib.py is the shipped copy of that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch), borrowed for the duration of the call;
+ *     the library owns only its packed fp16 weight copies inside esmb200_layer
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never synchronise
+ *   - return 0 on success, a negative ESMB200_E* code on failure; esmb200_last_error() gives the message of the last
+ *     failure on the calling thread. A device out-of-memory message starts with "CUDA out of memory" so that
+ *     scripts/fold.py:165-178's handler keeps working
+ *   - activations: residual stream x is fp32 [B, T, E] row-major (batch-major, i.e. the reference's (T,B,E)
+ *     transposed); MMA operands are fp16 with fp32 accumulation; LayerNorm / softmax / residual adds are fp32
+ *   - head_dim must be 64 (ESM-2 650M / 3B and the 6/12/30-layer test configs with E = 64*H); no CPU fallback
+ */
+#ifndef ESMB200_H_
+#define ESMB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESMB200_OK 0
+#define ESMB200_EINVAL -1   /* bad argument / unsupported shape */
+#define ESMB200_ECUDA -2    /* CUDA runtime or driver error */
+#define ESMB200_ENOMEM -3   /* device allocation failed ("CUDA out of memory ...") */
+#define ESMB200_EWORKSPACE -4 /* workspace too small */
+
+#define ESMB200_ABI_VERSION 1
+
+typedef struct esmb200_layer esmb200_layer; /* opaque: packed weights + TMA descriptors of one TransformerLayer */
+
+/* fp32 device pointers to one layer's parameters, nn.Linear layout weight[out,in] (state-dict names in comments,
+ * prefix "layers.{i}."; /root/reference/esm/modules.py:99-118, multihead_attention.py:109-113) */
+typedef struct esmb200_layer_weights {
+  int32_t embed_dim;   /* E */
+  int32_t num_heads;   /* H, E == 64*H */
+  int32_t ffn_dim;     /* F = 4E */
+  float ln_eps;        /* 1e-5 */
+  const float* ln1_weight; /* self_attn_layer_norm.weight [E] */
+  const float* ln1_bias;   /* self_attn_layer_norm.bias   [E] */
+  const float* q_weight;   /* self_attn.q_proj.weight [E,E] */
+  const float* q_bias;     /* self_attn.q_proj.bias   [E]   */
+  const float* k_weight;   /* self_attn.k_proj.weight [E,E] */
+  const float* k_bias;
+  const float* v_weight;   /* self_attn.v_proj.weight [E,E] */
+  const float* v_bias;
+  const float* out_weight; /* self_attn.out_proj.weight [E,E] */
+  const float* out_bias;
+  const float* ln2_weight; /* final_layer_norm.weight [E] */
+  const float* ln2_bias;
+  const float* fc1_weight; /* fc1.weight [F,E] */
+  const float* fc1_bias;   /* fc1.bias   [F]   */
+  const float* fc2_weight; /* fc2.weight [E,F] */
+  const float* fc2_bias;   /* fc2.bias   [E]   */
+} esmb200_layer_weights;
+
+int esmb200_abi_version(void);
+const char* esmb200_last_error(void);
+
+/* Packs one TransformerLayer's weights (fp32 -> fp16, [Wq;Wk;Wv] concatenated) on `stream`.
+ * Replaces TransformerLayer.__init__/_init_submodules state, modules.py:87-118. */
+int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_layer** out);
+int esmb200_layer_destroy(esmb200_layer* layer);
+
+/* Scratch bytes needed by esmb200_layer_forward / esmb200_stack_forward for a [B,T] batch. */
+size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t ffn_dim, int32_t B, int32_t T);
+
+/* One TransformerLayer.forward (modules.py:120-142), in place on x:
+ *     x += out_proj(attention(rope(q_proj(LN1 x) * d^-1/2), rope(k_proj(LN1 x)), v_proj(LN1 x)));
+ *     x += fc2(gelu(fc1(LN2 x)))
+ *   x          fp32 [B,T,E], updated in place
+ *   pad_mask   uint8/bool [B,T], nonzero = padding key (self_attn_padding_mask, esm2.py:82), or NULL
+ *   rope_cos/sin fp32 [T,32]: cos/sin(t * inv_freq[j]) (rotary_embedding.py:47-61), built by the caller
+ *   attn_probs fp32 [B,H,T,T] or NULL: softmax probabilities per head (need_head_weights=True,
+ *              multihead_attention.py:397-400, batch-major i.e. already transposed as esm2.py:121 does) */
+int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mask, int32_t B, int32_t T,
+                          const float* rope_cos, const float* rope_sin, float* attn_probs, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* The layer loop of ESM2.forward (esm2.py:111-121): runs n_layers layers in place on x.
+ *   repr_out[i]  NULL or fp32 [B,T,E]: copy of x after layer i (hidden_representations[i+1], esm2.py:117-118)
+ *   attn_out[i]  NULL or fp32 [B,H,T,T]: attention probabilities of layer i (esm2.py:119-121)
+ * either array pointer itself may be NULL. */
+int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float* x, const uint8_t* pad_mask,
+                          int32_t B, int32_t T, const float* rope_cos, const float* rope_sin,
+                          float* const* repr_out, float* const* attn_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Embedding prologue of ESM2.forward (esm2.py:84-95): gather from table [V,E], zero <mask> rows and rescale by
+ * 0.88/(1 - n_mask/n_nonpad) when token_dropout, zero pad rows. tokens int64 [B,T] -> x fp32 [B,T,E]. */
+int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, int32_t B, int32_t T, int32_t E,
+                         int32_t padding_idx, int32_t mask_idx, int32_t token_dropout, void* stream);
+
+/* torch.nn.LayerNorm over the last dim (ESM1bLayerNorm, modules.py:68-81; emb_layer_norm_after, esm2.py:123):
+ * fp32 [M,E] -> fp32 [M,E]. out may alias x. */
+int esmb200_layernorm(const float* x, const float* weight, const float* bias, float* out, int32_t M, int32_t E,
+                      float eps, void* stream);
+
+/* ---- single-kernel entry points (used by the parity tests and profiles; same kernels as above) ---- */
+
+/* out = epilogue(A[M,K] fp16 x W[N,K]^T fp16 + bias[N]);  epilogue: 0 qkv+rope -> fp16, 1 residual-add into fp32 out,
+ * 2 gelu -> fp16, 3 fp32, 4 gelu -> fp32. rope_* / T / E only for epilogue 0. K % 64 == 0, N % 64 == 0. */
+int esmb200_gemm_f16(int32_t epilogue, const void* a_f16, const void* w_f16, const float* bias, void* out, int32_t M,
+                     int32_t N, int32_t K, const float* rope_cos, const float* rope_sin, int32_t T, int32_t E,
+                     void* stream);
+
+/* ctx[B*T,E] fp16 = softmax(q k^T + key padding mask) v per head, from qkv fp16 [B*T,3E] (q pre-scaled, q/k rotated).
+ * scratch: at least esmb200_attention_scratch_bytes(B,T). attn_probs as in esmb200_layer_forward. */
+size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T);
+int esmb200_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, float* attn_probs, int32_t B,
+                      int32_t T, int32_t H, void* scratch, void* stream);
+
+/* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
+int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,
+                          float eps, void* stream);
+
+/* fp32 -> fp16 elementwise */
+int esmb200_convert_f16(const float* src, void* dst_f16, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESMB200_H_ */

@@ -1,0 +1,84 @@
+"""Per-kernel timing on the GPU box (CUDA events, warm-up, inputs larger than L2 or L2 flushed between reps).
+Prints one line per kernel with achieved TFLOP/s or GB/s. Developer tool; bench.py is the contract benchmark."""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from esm_b200 import _lib as L  # noqa: E402
+from esm_b200.model import rope_tables  # noqa: E402
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def S():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    B, T, H = int(os.environ.get("KB_B", 64)), 1024, 20
+    E, F = 64 * H, 4 * 64 * H
+    M = B * T
+    res = {}
+    x = torch.randn(M, E, device=dev)
+    w = torch.ones(E, device=dev)
+    bz = torch.zeros(E, device=dev)
+    xn = torch.empty(M, E, dtype=torch.float16, device=dev)
+    ms = timeit(lambda: L.check(lib.esmb200_layernorm_f16(P(x), P(w), P(bz), P(xn), M, E, 1e-5, S())))
+    res["layernorm_f16"] = {"ms": ms, "GB/s": M * E * 6 / ms / 1e6}
+
+    def gemm(epi, N, K, out_dtype, name):
+        a = torch.randn(M, K, device=dev).half()
+        wt = (torch.randn(N, K, device=dev) * K ** -0.5).half()
+        bias = torch.zeros(N, device=dev)
+        out = torch.zeros(M, N, dtype=out_dtype, device=dev)
+        inv = (1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))).to(dev)
+        cos, sin = rope_tables(inv, T)
+        ms = timeit(lambda: L.check(lib.esmb200_gemm_f16(epi, P(a), P(wt), P(bias), P(out), M, N, K, P(cos), P(sin), T, E, S())))
+        res[name] = {"ms": ms, "TFLOP/s": 2.0 * M * N * K / ms / 1e9}
+        # cuBLAS reference point for the same shape
+        ms2 = timeit(lambda: torch.matmul(a, wt.t()))
+        res[name]["cublas_fp16_TFLOP/s"] = 2.0 * M * N * K / ms2 / 1e9
+
+    gemm(L.EPI_QKV_ROPE, 3 * E, E, torch.float16, "gemm_qkv_rope")
+    gemm(L.EPI_BIAS_RESIDUAL, E, E, torch.float32, "gemm_out_residual")
+    gemm(L.EPI_BIAS_GELU, F, E, torch.float16, "gemm_fc1_gelu")
+    gemm(L.EPI_BIAS_RESIDUAL, E, F, torch.float32, "gemm_fc2_residual")
+
+    qkv = torch.randn(M, 3 * E, device=dev).half()
+    ctx = torch.empty(M, E, dtype=torch.float16, device=dev)
+    scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: L.check(lib.esmb200_attention(P(qkv), None, P(ctx), None, B, T, H, P(scratch), S())))
+    res["attention"] = {"ms": ms, "TFLOP/s": 4.0 * B * H * T * T * 64 / ms / 1e9}
+    for k, v in res.items():
+        print(k, json.dumps(v))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "kernel_bench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

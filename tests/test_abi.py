@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/esmb200.h declares; the product package
+never touches the oracle; the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "esmb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(esmb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from esm_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = header_symbols()
+    assert declared, "no symbols parsed from the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/esmb200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert _lib.load().esmb200_abi_version() == 1
+
+
+def test_workspace_size_is_pure_host_arithmetic():
+    from esm_b200 import _lib
+    lib = _lib.load()
+    small = lib.esmb200_workspace_bytes(1280, 5120, 1, 1024)
+    big = lib.esmb200_workspace_bytes(1280, 5120, 256, 1024)
+    assert 0 < small < big
+    assert big >= 256 * 1024 * (1280 * 2 + 5120 * 2)  # xn + h
+
+
+def test_product_package_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "esm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src:
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, f"product code references the oracle: {bad}"
+
+
+def test_no_cpu_fallback():
+    from esm_b200 import ESM2, _lib
+    model = ESM2(num_layers=1, embed_dim=128, attention_heads=2).eval()
+    tokens = torch.tensor([[0, 5, 6, 7, 2]])
+    with pytest.raises(_lib.Esmb200Error):
+        model(tokens)
+
+
+def test_head_dim_other_than_64_is_rejected():
+    from esm_b200 import ESM2
+    with pytest.raises(ValueError):
+        ESM2(num_layers=1, embed_dim=320, attention_heads=20)
+
+
+def test_state_dict_keys_match_reference_layout():
+    """keys/shapes the reference's checkpoints carry (SURVEY §7 data-layout notes; esm2.py:40-75)."""
+    from esm_b200 import ESM2
+    from oracle.weights import make_state_dict
+    model = ESM2(num_layers=2, embed_dim=128, attention_heads=2)
+    sd = make_state_dict(2, 128, 2)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    assert model.lm_head.weight is model.embed_tokens.weight

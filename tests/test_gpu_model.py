@@ -1,0 +1,108 @@
+"""GPU (-m gpu): the whole path through the reference-facing API (esm_b200.ESM2.forward -> C ABI -> sm_100a kernels)
+against (1) committed outputs of the unmodified reference (tests/golden), (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at the BASELINE.json model size.
+
+Stated tolerance (fp16 MMA operands, fp32 accumulate / residual / LayerNorm / softmax), per SURVEY §7 "hard parts":
+  representations: relative Frobenius error <= 2e-3, max-abs <= 2e-2 (values are O(1) after LayerNorm, O(10) before)
+  logits: max-abs <= 5e-2 on logits of magnitude O(10..100);  attentions: max-abs <= 2e-3;  contacts: max-abs <= 5e-3
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_FRO = 2e-3
+
+
+def rel_fro(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def build_model(L, E, H, seed=0):
+    from esm_b200 import ESM2
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(L, E, H, seed=seed)
+    model = ESM2(num_layers=L, embed_dim=E, attention_heads=H)
+    model.load_state_dict(sd, strict=True)
+    return model.eval().cuda(), sd
+
+
+@pytest.mark.parametrize("name", ["tiny_L2_E128_H2", "mid_L3_E256_H4", "nopad_L2_E128_H2"])
+def test_against_reference_golden(name, golden_dir):
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg = fx["config"]
+    model, _ = build_model(cfg["num_layers"], cfg["embed_dim"], cfg["attention_heads"], cfg["seed"])
+    out = model(fx["tokens"].cuda(), repr_layers=fx["repr_layers"], need_head_weights=True, return_contacts=True)
+    torch.cuda.synchronize()
+    assert set(out.keys()) == {"logits", "representations", "attentions", "contacts"}
+    for k, ref in fx["representations"].items():
+        got = out["representations"][k].cpu()
+        assert got.shape == ref.shape
+        assert rel_fro(got, ref) <= REL_FRO, (k, rel_fro(got, ref))
+        assert float((got - ref).abs().max()) <= 2e-2 * max(1.0, float(ref.abs().max()) / 4)
+    assert float((out["logits"].cpu() - fx["logits"]).abs().max()) <= 5e-2
+    L, H = cfg["num_layers"], cfg["attention_heads"]
+    sub = out["attentions"][:, [0, L - 1]][:, :, [0, H - 1]].cpu()
+    assert float((sub - fx["attentions_sub"]).abs().max()) <= 2e-3
+    if fx["attentions"] is not None:
+        assert float((out["attentions"].cpu() - fx["attentions"]).abs().max()) <= 2e-3
+    assert float((out["contacts"].cpu() - fx["contacts"]).abs().max()) <= 5e-3
+
+
+def test_against_oracle_650M_width():
+    """4 layers at the 650M width (E=1280, H=20, F=5120), ragged batch, T=300 (3 key blocks, last one partial)."""
+    from oracle import esm2_oracle
+    from oracle.weights import make_tokens
+    L, E, H = 4, 1280, 20
+    model, sd = build_model(L, E, H)
+    tokens = make_tokens([298, 140, 5], 300, seed=7, n_mask=2)
+    ref = esm2_oracle.esm2_forward(sd, L, H, tokens, repr_layers=[0, 2, 4])
+    out = model(tokens.cuda(), repr_layers=[0, 2, 4])
+    for k in (0, 2, 4):
+        r = rel_fro(out["representations"][k].cpu(), ref["representations"][k])
+        assert r <= REL_FRO, (k, r)
+    assert float((out["logits"].cpu() - ref["logits"]).abs().max()) <= 5e-2
+    assert "attentions" not in out and "contacts" not in out
+
+
+def test_layer_level_interface_matches_reference_contract():
+    """TransformerLayer.forward(x (T,B,E), self_attn_padding_mask (B,T)) -> (x (T,B,E), attn (H,B,T,T) | None),
+    modules.py:120-142."""
+    from oracle import esm2_oracle
+    model, sd = build_model(1, 128, 2)
+    T, B, E = 50, 3, 128
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(T, B, E, generator=g)
+    pad = torch.zeros(B, T, dtype=torch.bool)
+    pad[1, 30:] = True
+    ref, probs = esm2_oracle.transformer_layer(x.transpose(0, 1), sd, "layers.0.", 2, pad, True)
+    y, attn = model.layers[0](x.cuda(), self_attn_padding_mask=pad.cuda(), need_head_weights=True)
+    assert y.shape == (T, B, E) and attn.shape == (2, B, T, T)
+    assert rel_fro(y.cpu().transpose(0, 1), ref) <= REL_FRO
+    assert float((attn.cpu().transpose(0, 1) - probs).abs().max()) <= 2e-3
+    y2, attn2 = model.layers[0](x.cuda(), self_attn_padding_mask=pad.cuda())
+    assert attn2 is None and torch.equal(y2, y)
+
+
+def test_full_size_properties_650M():
+    """BASELINE.json configs[1] model (33 x 1280 x 20 heads) at L=1024: properties that need no CPU oracle run.
+    (a) a sequence embedded alone equals the same sequence embedded inside a ragged batch, bit for bit
+        (sequences are independent, esm2.py:77-144; padding keys get exactly zero probability);
+    (b) batch order does not matter; (c) outputs are finite and post-LayerNorm statistics are sane."""
+    from oracle.weights import make_tokens
+    torch.manual_seed(0)
+    from esm_b200 import pretrained
+    model, alphabet = pretrained.esm2_t33_650M_UR50D()
+    model = model.cuda()
+    tokens = make_tokens([1022, 700, 1022, 333], 1024, seed=11).cuda()
+    out = model(tokens, repr_layers=[33])["representations"][33]
+    assert out.shape == (4, 1024, 1280) and bool(torch.isfinite(out).all())
+    perm = torch.tensor([2, 0, 3, 1], device="cuda")
+    out_p = model(tokens[perm], repr_layers=[33])["representations"][33]
+    assert torch.equal(out_p, out[perm])
+    alone = model(tokens[1:2, :702], repr_layers=[33])["representations"][33]
+    assert torch.equal(alone[0], out[1, :702])
+    row_mean = out[0].mean(-1).abs().max()
+    assert float(row_mean) < 1.0
