@@ -25,11 +25,15 @@ EXPORTS = (
     "esmb200_stack_forward",
     "esmb200_embed_tokens",
     "esmb200_layernorm",
+    "esmb200_mean_pool",
     "esmb200_gemm_f16",
     "esmb200_attention_scratch_bytes",
     "esmb200_attention",
     "esmb200_layernorm_f16",
     "esmb200_convert_f16",
+    "esmb200_launch_count",
+    "esmb200_profile_enable",
+    "esmb200_profile_read",
 )
 
 EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU, EPI_BIAS_F32, EPI_BIAS_GELU_F32 = range(5)
@@ -91,6 +95,8 @@ def _declare(lib):
                                          c_int32, c_void_p]
     lib.esmb200_layernorm.restype = c_int32
     lib.esmb200_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]
+    lib.esmb200_mean_pool.restype = c_int32
+    lib.esmb200_mean_pool.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.esmb200_layernorm_f16.restype = c_int32
     lib.esmb200_layernorm_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]
     lib.esmb200_gemm_f16.restype = c_int32
@@ -101,6 +107,12 @@ def _declare(lib):
     lib.esmb200_attention.restype = c_int32
     lib.esmb200_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                       c_void_p]
+    lib.esmb200_launch_count.restype = ctypes.c_longlong
+    lib.esmb200_launch_count.argtypes = []
+    lib.esmb200_profile_enable.restype = c_int32
+    lib.esmb200_profile_enable.argtypes = [c_int32]
+    lib.esmb200_profile_read.restype = c_int32
+    lib.esmb200_profile_read.argtypes = [POINTER(c_int32), POINTER(c_float), c_int32]
     lib.esmb200_convert_f16.restype = c_int32
     lib.esmb200_convert_f16.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
 

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "attention.cuh"
 #include "common.cuh"
@@ -41,6 +42,38 @@ int fail_cuda(cudaError_t e, const char* what) {
     cudaError_t _e = (expr);                            \
     if (_e != cudaSuccess) return fail_cuda(_e, #expr); \
   } while (0)
+
+
+// ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) --------------------
+enum ProfTag : int { T_LN1 = 0, T_QKV, T_ATTN, T_OUT, T_LN2, T_FC1, T_FC2, T_KEYBITS, T_EMBED, T_LN_F32, T_PROBS,
+                     T_CONVERT, T_GEMM_OTHER, T_MEANPOOL, T_COUNT };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // pairs (start, stop)
+  std::vector<int> tag;
+  size_t used = 0;              // events used
+  long long launches = 0;       // kernels launched by this library since load
+};
+Profiler g_prof;
+
+struct ProfScope {
+  cudaStream_t st;
+  bool rec;
+  ProfScope(int tag, cudaStream_t s) : st(s), rec(false) {
+    ++g_prof.launches;
+    if (g_prof.on && g_prof.used + 2 <= g_prof.ev.size()) {
+      rec = true;
+      g_prof.tag.push_back(tag);
+      cudaEventRecord(g_prof.ev[g_prof.used], st);
+    }
+  }
+  ~ProfScope() {
+    if (rec) {
+      cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+      g_prof.used += 2;
+    }
+  }
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -105,7 +138,9 @@ int check_device() {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st,
+                int tag = T_GEMM_OTHER) {
+  ProfScope ps(tag, st);
   cudaError_t e;
   switch (epi) {
     case EPI_QKV_ROPE: e = launch_gemm_epi<EPI_QKV_ROPE>(ta, tb, p, num_sms(), st); break;
@@ -149,6 +184,7 @@ AttnScratch carve_attn_scratch(void* scratch, int B, int T, int H) {
 
 int run_key_bits(const uint8_t* pad_mask, const AttnScratch& s, int B, int T, cudaStream_t st) {
   const int wpb = 4;
+  ProfScope ps(T_KEYBITS, st);
   key_bits_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(pad_mask, s.keybits, s.kvlen, B, T, s.words);
   CK(cudaGetLastError());
   return ESMB200_OK;
@@ -166,7 +202,11 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
   ap.ctx = static_cast<__half*>(ctx);
   ap.row_max = probs ? s.row_max : nullptr;
   ap.row_sum = probs ? s.row_sum : nullptr;
-  cudaError_t e = launch_attention(tq, ap, st);
+  cudaError_t e;
+  {
+    ProfScope ps(T_ATTN, st);
+    e = launch_attention(tq, ap, st);
+  }
   if (e != cudaSuccess) return fail_cuda(e, "attention launch");
   if (probs) {
     if ((size_t)B * H > 65535) return fail(ESMB200_EINVAL, "need_head_weights: B*H must be <= 65535");
@@ -174,7 +214,10 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
     pp.B = B; pp.T = T; pp.H = H; pp.E = E;
     pp.keybits = s.keybits; pp.kvlen = s.kvlen; pp.words = s.words;
     pp.row_max = s.row_max; pp.row_sum = s.row_sum; pp.probs = probs;
-    e = launch_attention_probs(tq, pp, st);
+    {
+      ProfScope ps(T_PROBS, st);
+      e = launch_attention_probs(tq, pp, st);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "attention probs launch");
   }
   return ESMB200_OK;
@@ -210,6 +253,7 @@ int esmb200_convert_f16(const float* src, void* dst, size_t n, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps(T_CONVERT, st);
   convert_f32_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, static_cast<__half*>(dst), n);
   CK(cudaGetLastError());
   return ESMB200_OK;
@@ -327,14 +371,17 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   const int M = B * T;
   cudaError_t e;
   // LN1 -> fp16 (modules.py:124)
-  e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+  {
+    ProfScope ps(T_LN1, st);
+    e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+  }
   if (e != cudaSuccess) return fail_cuda(e, "layernorm1");
   // q,k,v projections + bias + q scale + RoPE (multihead_attention.py:258-261,354-355)
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
-  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, g, st);
+  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, g, st, T_QKV);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
   rc = run_attention(ws.qkv, ws.ctx, attn_probs, ws.as, B, T, H, st);
@@ -342,20 +389,23 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, g, st);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, g, st, T_OUT);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
-  e = launch_layernorm<true>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
+  {
+    ProfScope ps(T_LN2, st);
+    e = launch_layernorm<true>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
+  }
   if (e != cudaSuccess) return fail_cuda(e, "layernorm2");
   // fc1 + GELU (modules.py:138)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
-  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, g, st);
+  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, g, st, T_FC1);
   if (rc) return rc;
   // fc2 + residual (modules.py:139-140)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, g, st);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, g, st, T_FC2);
   return rc;
 }
 
@@ -412,6 +462,7 @@ int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, in
                          int32_t padding_idx, int32_t mask_idx, int32_t token_dropout, void* stream) {
   if (!tokens || !table || !x) return fail(ESMB200_EINVAL, "null argument");
   if (B <= 0 || T <= 0 || E % 4 != 0) return fail(ESMB200_EINVAL, "bad shape");
+  ProfScope ps(T_EMBED, static_cast<cudaStream_t>(stream));
   embed_tokens_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, table, x, T, E, padding_idx, mask_idx,
                                                                         token_dropout);
   CK(cudaGetLastError());
@@ -421,6 +472,7 @@ int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, in
 int esmb200_layernorm(const float* x, const float* weight, const float* bias, float* out, int32_t M, int32_t E,
                       float eps, void* stream) {
   if (!x || !weight || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
+  ProfScope ps(T_LN_F32, static_cast<cudaStream_t>(stream));
   cudaError_t e = launch_layernorm<false>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "layernorm");
   return ESMB200_OK;
@@ -429,6 +481,7 @@ int esmb200_layernorm(const float* x, const float* weight, const float* bias, fl
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out, int32_t M, int32_t E,
                           float eps, void* stream) {
   if (!x || !weight || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
+  ProfScope ps(T_LN1, static_cast<cudaStream_t>(stream));
   cudaError_t e = launch_layernorm<true>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "layernorm_f16");
   return ESMB200_OK;
@@ -466,6 +519,50 @@ int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float
   rc = run_key_bits(pad_mask, s, B, T, st);
   if (rc) return rc;
   return run_attention(qkv, ctx, attn_probs, s, B, T, H, st);
+}
+
+
+int esmb200_mean_pool(const float* x, const int32_t* lengths, float* out, int32_t B, int32_t T, int32_t E,
+                      void* stream) {
+  if (!x || !lengths || !out) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || T < 2 || E <= 0 || B > 65535) return fail(ESMB200_EINVAL, "bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(T_MEANPOOL, st);
+  dim3 grid((E + 255) / 256, B);
+  mean_pool_kernel<<<grid, 256, 0, st>>>(x, lengths, out, T, E);
+  CK(cudaGetLastError());
+  return ESMB200_OK;
+}
+
+long long esmb200_launch_count(void) { return g_prof.launches; }
+
+int esmb200_profile_enable(int32_t max_launches) {
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.tag.clear();
+  g_prof.used = 0;
+  g_prof.on = max_launches > 0;
+  for (int i = 0; i < 2 * max_launches; ++i) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    g_prof.ev.push_back(e);
+  }
+  return ESMB200_OK;
+}
+
+int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records) {
+  const int n = (int)(g_prof.used / 2);
+  int out = 0;
+  for (int i = 0; i < n && out < max_records; ++i, ++out) {
+    CK(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    tags[out] = g_prof.tag[i];
+    ms[out] = t;
+  }
+  g_prof.used = 0;
+  g_prof.tag.clear();
+  return out;
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 //   embed_tokens      esm/model/esm2.py:84-95 (embedding gather, <mask> zeroing, token-dropout rescale
 //                     0.88/(1-mask_ratio), pad zeroing)
 //   key_bits          esm/model/esm2.py:82 + multihead_attention.py:368-374 (key padding mask) packed to 1 bit/key
+//   mean_pool         scripts/extract.py:116-119 per-sequence mean representation
 //   convert_f32_f16   weight packing (fp32 nn.Linear weights -> fp16 MMA operands)
 #pragma once
 
@@ -141,6 +142,28 @@ __global__ void key_bits_kernel(const uint8_t* __restrict__ pad_mask, uint32_t* 
     if (bits) last = w * 32 + (32 - __clz(bits));
   }
   if (lane == 0) kvlen[b] = last;
+}
+
+// Per-sequence mean over residues (scripts/extract.py:116-119: representations[i, 1 : len+1].mean(0)).
+// grid (ceil(E/256), B); thread = one column, rows streamed with coalesced 1 KB warp-rows.
+__global__ void __launch_bounds__(256)
+mean_pool_kernel(const float* __restrict__ x, const int* __restrict__ lengths, float* __restrict__ out, int T, int E) {
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= E) return;
+  int n = lengths[b];
+  n = n < 0 ? 0 : (n > T - 1 ? T - 1 : n);
+  const float* xp = x + ((size_t)b * T + 1) * E + col;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int t = 0;
+  for (; t + 4 <= n; t += 4) {
+    a0 += xp[(size_t)(t + 0) * E];
+    a1 += xp[(size_t)(t + 1) * E];
+    a2 += xp[(size_t)(t + 2) * E];
+    a3 += xp[(size_t)(t + 3) * E];
+  }
+  for (; t < n; ++t) a0 += xp[(size_t)t * E];
+  out[(size_t)b * E + col] = ((a0 + a1) + (a2 + a3)) / (float)n;
 }
 
 __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {

@@ -106,6 +106,11 @@ int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, in
 int esmb200_layernorm(const float* x, const float* weight, const float* bias, float* out, int32_t M, int32_t E,
                       float eps, void* stream);
 
+/* Per-sequence mean representation, scripts/extract.py:116-119: out[b] = mean_t x[b, 1 : 1+lengths[b]] (residues only,
+ * <cls> at position 0 excluded). x fp32 [B,T,E], lengths int32 [B] (device), out fp32 [B,E]. */
+int esmb200_mean_pool(const float* x, const int32_t* lengths, float* out, int32_t B, int32_t T, int32_t E,
+                      void* stream);
+
 /* ---- single-kernel entry points (used by the parity tests and profiles; same kernels as above) ---- */
 
 /* out = epilogue(A[M,K] fp16 x W[N,K]^T fp16 + bias[N]);  epilogue: 0 qkv+rope -> fp16, 1 residual-add into fp32 out,
@@ -123,6 +128,17 @@ int esmb200_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f1
 /* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,
                           float eps, void* stream);
+
+/* ---- launch accounting and per-launch timing (bench.py roofline numbers) ----
+ * esmb200_launch_count: kernels launched by this library since it was loaded.
+ * esmb200_profile_enable(n): n > 0 brackets each of the next n launches with CUDA events on the launch stream
+ *   (0 disables and frees the events); esmb200_profile_read returns up to max_records (tag, milliseconds) pairs,
+ *   synchronising on the recorded events, and resets the record list.
+ *   tags: 0 LN1->f16, 1 QKV+RoPE GEMM, 2 attention, 3 out-proj GEMM, 4 LN2->f16, 5 fc1+GELU GEMM, 6 fc2 GEMM,
+ *         7 key bits, 8 embed, 9 LayerNorm fp32, 10 attention probs, 11 convert, 12 other GEMM, 13 mean pool */
+long long esmb200_launch_count(void);
+int esmb200_profile_enable(int32_t max_launches);
+int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records);
 
 /* fp32 -> fp16 elementwise */
 int esmb200_convert_f16(const float* src, void* dst_f16, size_t n, void* stream);
