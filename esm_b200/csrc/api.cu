@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -19,6 +20,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 using namespace esmb200;
 
@@ -91,18 +93,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D fp16 row-major [rows, cols] (cols contiguous), box = {64 cols (128 B), box_rows}, 128B swizzle.
-int make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                  uint32_t box_rows) {
+// 2D row-major [rows, cols] (cols contiguous) of fp16 (esize 2) or fp32 (esize 4);
+// box = {128 bytes of columns, box_rows}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ESMB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_elems * 2) % 16 != 0)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld_elems * esize) % 16 != 0)
     return fail(ESMB200_EINVAL, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -112,6 +116,21 @@ int make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t col
     return fail(ESMB200_ECUDA, buf);
   }
   return ESMB200_OK;
+}
+
+int make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                  uint32_t box_rows) {
+  return make_tmap_2d(map, ptr, 2, rows, cols, ld_elems, box_rows);
+}
+
+// GEMM implementation: 2 = CTA-pair kernel (gemm2.cuh, default), 1 = single-CTA kernel (gemm.cuh).
+int gemm_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("ESMB200_GEMM");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
 }
 
 int num_sms() {
@@ -138,10 +157,22 @@ int check_device() {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st,
-                int tag = T_GEMM_OTHER) {
+int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const GemmParams& p,
+                cudaStream_t st, int tag = T_GEMM_OTHER) {
   ProfScope ps(tag, st);
   cudaError_t e;
+  if (tout != nullptr) {
+    switch (epi) {
+      case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_BIAS_GELU: e = launch_gemm2_epi<EPI_BIAS_GELU>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_BIAS_F32: e = launch_gemm2_epi<EPI_BIAS_F32>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_BIAS_GELU_F32: e = launch_gemm2_epi<EPI_BIAS_GELU_F32>(ta, tb, *tout, p, num_sms(), st); break;
+      default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");
+    return ESMB200_OK;
+  }
   switch (epi) {
     case EPI_QKV_ROPE: e = launch_gemm_epi<EPI_QKV_ROPE>(ta, tb, p, num_sms(), st); break;
     case EPI_BIAS_RESIDUAL: e = launch_gemm_epi<EPI_BIAS_RESIDUAL>(ta, tb, p, num_sms(), st); break;
@@ -239,7 +270,7 @@ struct esmb200_layer {
   __half* w_fc1;  // [F,E]
   __half* w_fc2;  // [E,F]
   float* b_qkv;   // [3E]
-  CUtensorMap tm_qkv, tm_out, tm_fc1, tm_fc2;  // B operands, box {64, 256}
+  CUtensorMap tm_qkv, tm_out, tm_fc1, tm_fc2;  // B operands, box {64, 256 rows} (v1) or {64, 128 rows} (v2)
 };
 
 extern "C" {
@@ -309,10 +340,11 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
     if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + 2 * E, w->v_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) rc = fail_cuda(e, "bias pack");
   }
-  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)E, E, E, gemm_cfg::BLOCK_N);
-  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, E, E, gemm_cfg::BLOCK_N);
-  if (!rc) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, gemm_cfg::BLOCK_N);
-  if (!rc) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, gemm_cfg::BLOCK_N);
+  const uint32_t wbox = gemm_version() == 2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N;
+  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)E, E, E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, E, E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, wbox);
   if (rc) {
     esmb200_layer_destroy(L);
     return rc;
@@ -362,7 +394,9 @@ int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int F, 
 }
 
 struct ActMaps {
-  CUtensorMap xn, ctx, h;
+  CUtensorMap xn, ctx, h;       // A operands (fp16, box {64,128}); h doubles as fc1's output map
+  CUtensorMap qkv_out, x_out;   // v2 epilogue outputs: qkv fp16 [M,3E] box {64,128}; x fp32 [M,E] box {32,128}
+  bool v2;
 };
 
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
@@ -381,7 +415,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
-  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, g, st, T_QKV);
+  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
   rc = run_attention(ws.qkv, ws.ctx, attn_probs, ws.as, B, T, H, st);
@@ -389,7 +423,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, g, st, T_OUT);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
   {
@@ -400,19 +434,22 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // fc1 + GELU (modules.py:138)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
-  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, g, st, T_FC1);
+  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.v2 ? &am.h : nullptr, g, st, T_FC1);
   if (rc) return rc;
   // fc2 + residual (modules.py:139-140)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, g, st, T_FC2);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.v2 ? &am.x_out : nullptr, g, st, T_FC2);
   return rc;
 }
 
-int make_act_maps(ActMaps* am, const Workspace& ws, int E, int F, int M) {
+int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int F, int M) {
+  am->v2 = gemm_version() == 2;
   int rc = make_tmap_f16(&am->xn, ws.xn, M, E, E, gemm_cfg::BLOCK_M);
   if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, E, E, gemm_cfg::BLOCK_M);
   if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, F, F, gemm_cfg::BLOCK_M);
+  if (!rc && am->v2) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
+  if (!rc && am->v2) rc = make_tmap_2d(&am->x_out, x, 4, M, E, E, 128);
   return rc;
 }
 }  // namespace
@@ -435,7 +472,7 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   rc = carve_workspace(&ws, workspace, workspace_bytes, E, F, B, T);
   if (rc) return rc;
   ActMaps am;
-  rc = make_act_maps(&am, ws, E, F, B * T);
+  rc = make_act_maps(&am, ws, x, E, F, B * T);
   if (rc) return rc;
   rc = run_key_bits(pad_mask, ws.as, B, T, st);
   if (rc) return rc;
@@ -497,15 +534,18 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
   if (rc) return rc;
   if (epilogue == EPI_QKV_ROPE && (!rope_cos || !rope_sin || T <= 0 || E <= 0 || E % 64 != 0 || N != 3 * E))
     return fail(ESMB200_EINVAL, "qkv epilogue needs rope tables, T and N == 3E");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tout;
+  const bool v2 = gemm_version() == 2;
+  const bool out_f16 = (epilogue == EPI_QKV_ROPE || epilogue == EPI_BIAS_GELU);
   rc = make_tmap_f16(&ta, a, M, K, K, gemm_cfg::BLOCK_M);
-  if (!rc) rc = make_tmap_f16(&tb, w, N, K, K, gemm_cfg::BLOCK_N);
+  if (!rc) rc = make_tmap_f16(&tb, w, N, K, K, v2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N);
+  if (!rc && v2) rc = make_tmap_2d(&tout, out, out_f16 ? 2 : 4, M, N, N, 128);
   if (rc) return rc;
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = N;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
-  return launch_gemm(epilogue, ta, tb, g, static_cast<cudaStream_t>(stream));
+  return launch_gemm(epilogue, ta, tb, v2 ? &tout : nullptr, g, static_cast<cudaStream_t>(stream));
 }
 
 int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,

@@ -1,0 +1,305 @@
+// esm_b200 — GEMM v2: CTA-pair (cta_group::2) tcgen05 GEMM with TMA-store / TMA-reduce epilogues (sm_100a).
+//
+// Same math and epilogues as gemm.cuh (see there for the reference lines each epilogue replaces); what changes is how
+// the SM pair is driven:
+//   * a cluster of 2 CTAs owns a 256x256 output tile; each CTA TMA-loads 128 rows of A and 128 rows (half of N) of B
+//     per 64-wide K slab, and ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 (UMMA 256x256x16), so every
+//     byte of B staged in shared memory feeds both tensor cores (half the smem fill traffic per FLOP of v1);
+//   * 5-stage TMA ring (32 KB/stage/CTA), 2x256-column TMEM accumulator double buffer per CTA;
+//   * epilogue: TMEM -> registers (bias / q-scale+RoPE / erf-GELU) -> 128B-swizzled smem tile -> one TMA bulk store
+//     per 128x64 fp16 (or 128x32 fp32) block; the residual add is a TMA *reduce-add* into the fp32 stream, so x is
+//     never read back into the SM.
+#pragma once
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace esmb200 {
+
+namespace gemm2_cfg {
+constexpr int BLOCK_M = 128;   // rows per CTA
+constexpr int PAIR_M = 256;    // rows per cluster tile
+constexpr int BLOCK_N = 256;
+constexpr int HALF_N = 128;    // B rows loaded by each CTA
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 5;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int NUM_THREADS = 384;
+constexpr int STG_BYTES = 128 * 128;  // 128 rows x 128 B staging tile
+constexpr int NUM_STG = 4;            // 2 per 128-column half
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STG * STG_BYTES + 1024 + 256;
+}  // namespace gemm2_cfg
+
+// thread `row` writes its 8 x 16-byte chunks of a 128-byte row into a SWIZZLE_128B staging tile
+__device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, const uint32_t (&v)[32]) {
+  const uint32_t base = smem_u32(stg) + row * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t addr = base + (((uint32_t)c ^ (row & 7u)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                 "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                 : "memory");
+  }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using namespace gemm2_cfg;
+  constexpr bool OUT_F16 = (EPI == EPI_QKV_ROPE || EPI == EPI_BIAS_GELU);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_stg = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_STG * STG_BYTES);
+  uint64_t* full_bar = bars;                              // [STAGES]     used in the leader CTA only
+  uint64_t* empty_bar = bars + STAGES;                    // [STAGES]     one per CTA
+  uint64_t* tfull_bar = bars + 2 * STAGES;                // [ACC_STAGES] one per CTA
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] used in the leader CTA only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const uint32_t warp = threadIdx.x / 32;
+  const uint32_t lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int tiles_m = (p.M + PAIR_M - 1) / PAIR_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);   // one arrival per CTA of the pair (+ the transaction bytes of both)
+      mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane per CTA) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        const int a_row = m_blk * PAIR_M + rank * BLOCK_M;
+        const int b_row = n_blk * BLOCK_N + rank * HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, a_row);
+          tma_load_2d_pair(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one lane of the leader CTA) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR_M, BLOCK_N, false);
+      uint32_t stage = 0, phase = 0;
+      int iter = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+        const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), 1024, 0);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_pair(&empty_bar[stage], 0b11);
+          if (kb == num_kb - 1) tc_commit_pair(&tfull_bar[as], 0b11);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> regs -> swizzled smem -> TMA store / reduce =====================
+    const uint32_t ew = warp - 4;
+    const uint32_t quarter = warp % 4;
+    const uint32_t chalf = ew / 4;
+    const uint32_t row_local = quarter * 32 + lane;
+    const bool issuer = (ew % 4 == 0) && lane == 0;
+    const uint32_t bar_id = 1 + chalf;
+    uint32_t store_iter = 0;
+    int iter = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row0 = m_blk * PAIR_M + rank * BLOCK_M;
+      const int row = row0 + row_local;
+      const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + chalf * 128;
+      const int col0 = n_blk * BLOCK_N + chalf * 128;
+
+      if constexpr (OUT_F16) {
+        int t = 0;
+        if constexpr (EPI == EPI_QKV_ROPE) t = (row < p.M) ? (row % p.T) : 0;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + g * 64;
+          if (col >= p.N) break;  // uniform over the 4 warps of this column half
+          uint32_t lo[32], hi[32], outv[32];
+          tmem_ld_32x32b_x32(taddr0 + g * 64, lo);
+          tmem_ld_32x32b_x32(taddr0 + g * 64 + 32, hi);
+          tmem_wait_ld();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          if constexpr (EPI == EPI_QKV_ROPE) {
+            const int sect = col / p.E;  // 0 q, 1 k, 2 v
+            const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
+            const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
+            const float sc = (sect == 0) ? p.q_scale : 1.0f;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
+              const float x1[4] = {__uint_as_float(lo[4 * j4 + 0]) + bl.x, __uint_as_float(lo[4 * j4 + 1]) + bl.y,
+                                   __uint_as_float(lo[4 * j4 + 2]) + bl.z, __uint_as_float(lo[4 * j4 + 3]) + bl.w};
+              const float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
+                                   __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
+              float y1[4], y2[4];
+              if (sect < 2) {
+                const float4 c = __ldg(cs4 + j4), s = __ldg(sn4 + j4);
+                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a = x1[e] * sc, b = x2[e] * sc;
+                  y1[e] = a * cc[e] - b * ss[e];
+                  y2[e] = b * cc[e] + a * ss[e];
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { y1[e] = x1[e]; y2[e] = x2[e]; }
+              }
+              outv[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
+              outv[2 * j4 + 1] = pack_half2(y1[2], y1[3]);
+              outv[16 + 2 * j4 + 0] = pack_half2(y2[0], y2[1]);
+              outv[16 + 2 * j4 + 1] = pack_half2(y2[2], y2[3]);
+            }
+          } else {  // EPI_BIAS_GELU
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 bl = __ldg(b4 + v), bh = __ldg(b4 + 8 + v);
+              outv[2 * v] = pack_half2(gelu_erf(__uint_as_float(lo[4 * v + 0]) + bl.x),
+                                       gelu_erf(__uint_as_float(lo[4 * v + 1]) + bl.y));
+              outv[2 * v + 1] = pack_half2(gelu_erf(__uint_as_float(lo[4 * v + 2]) + bl.z),
+                                           gelu_erf(__uint_as_float(lo[4 * v + 3]) + bl.w));
+              outv[16 + 2 * v] = pack_half2(gelu_erf(__uint_as_float(hi[4 * v + 0]) + bh.x),
+                                            gelu_erf(__uint_as_float(hi[4 * v + 1]) + bh.y));
+              outv[16 + 2 * v + 1] = pack_half2(gelu_erf(__uint_as_float(hi[4 * v + 2]) + bh.z),
+                                                gelu_erf(__uint_as_float(hi[4 * v + 3]) + bh.w));
+            }
+          }
+          uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+          if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
+          named_bar_sync(bar_id, 128);
+          stage_row_sw128(stg, row_local, outv);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer && row0 < p.M) {  // rows past M are clipped by the tensor map; a fully outside box is skipped
+            tma_store_2d(&tmap_out, stg, col, row0);
+            tma_store_commit();
+          }
+          ++store_iter;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = col0 + c * 32;
+          if (col >= p.N) break;
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(taddr0 + c * 32, acc);
+          tmem_wait_ld();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const float4 b = __ldg(b4 + v);
+            float o0 = __uint_as_float(acc[4 * v + 0]) + b.x, o1 = __uint_as_float(acc[4 * v + 1]) + b.y;
+            float o2 = __uint_as_float(acc[4 * v + 2]) + b.z, o3 = __uint_as_float(acc[4 * v + 3]) + b.w;
+            if constexpr (EPI == EPI_BIAS_GELU_F32) {
+              o0 = gelu_erf(o0); o1 = gelu_erf(o1); o2 = gelu_erf(o2); o3 = gelu_erf(o3);
+            }
+            acc[4 * v + 0] = __float_as_uint(o0); acc[4 * v + 1] = __float_as_uint(o1);
+            acc[4 * v + 2] = __float_as_uint(o2); acc[4 * v + 3] = __float_as_uint(o3);
+          }
+          uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+          if (issuer) tma_store_wait_read<1>();
+          named_bar_sync(bar_id, 128);
+          stage_row_sw128(stg, row_local, acc);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer && row0 < p.M) {
+            if constexpr (EPI == EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmap_out, stg, col, row0);
+            else tma_store_2d(&tmap_out, stg, col, row0);
+            tma_store_commit();
+          }
+          ++store_iter;
+        }
+      }
+      // every TMEM read of this warp has completed -> one arrival per warp on the leader's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI>
+inline cudaError_t launch_gemm2_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
+                                    const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using namespace gemm2_cfg;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm2_f16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = ((p.M + PAIR_M - 1) / PAIR_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm2_f16_kernel<EPI><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tout, p);
+  return cudaGetLastError();
+}
+
+}  // namespace esmb200
