@@ -44,14 +44,18 @@ def main():
     E, F = 64 * H, 4 * 64 * H
     M = B * T
     res = {}
+    only = os.environ.get("KB_ONLY")  # run a single kernel (for ncu captures)
     x = torch.randn(M, E, device=dev)
     w = torch.ones(E, device=dev)
     bz = torch.zeros(E, device=dev)
     xn = torch.empty(M, E, dtype=torch.float16, device=dev)
-    ms = timeit(lambda: L.check(lib.esmb200_layernorm_f16(P(x), P(w), P(bz), P(xn), M, E, 1e-5, S())))
-    res["layernorm_f16"] = {"ms": ms, "GB/s": M * E * 6 / ms / 1e6}
+    if not only or only == "layernorm_f16":
+        ms = timeit(lambda: L.check(lib.esmb200_layernorm_f16(P(x), P(w), P(bz), P(xn), M, E, 1e-5, S())))
+        res["layernorm_f16"] = {"ms": ms, "GB/s": M * E * 6 / ms / 1e6}
 
     def gemm(epi, N, K, out_dtype, name):
+        if only and only != name:
+            return
         a = torch.randn(M, K, device=dev).half()
         wt = (torch.randn(N, K, device=dev) * K ** -0.5).half()
         bias = torch.zeros(N, device=dev)
@@ -66,9 +70,12 @@ def main():
 
     gemm(L.EPI_QKV_ROPE, 3 * E, E, torch.float16, "gemm_qkv_rope")
     gemm(L.EPI_BIAS_RESIDUAL, E, E, torch.float32, "gemm_out_residual")
+    gemm(L.EPI_BIAS_F32, E, E, torch.float32, "gemm_out_plainstore_f32")
     gemm(L.EPI_BIAS_GELU, F, E, torch.float16, "gemm_fc1_gelu")
     gemm(L.EPI_BIAS_RESIDUAL, E, F, torch.float32, "gemm_fc2_residual")
 
+    if only and only != "attention":
+        print(json.dumps(res)); return
     qkv = torch.randn(M, 3 * E, device=dev).half()
     ctx = torch.empty(M, E, dtype=torch.float16, device=dev)
     scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)

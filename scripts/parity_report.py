@@ -37,7 +37,7 @@ def main():
         sub = out["attentions"][:, [0, L - 1]][:, :, [0, H - 1]]
         r["attentions_sub"] = metrics(sub, fx["attentions_sub"])
         rep[name] = r
-    for qk_gain in (1.0, 3.0):
+    for qk_gain in (1.0, 1.5, 3.0):
         L, E, H = 6, 1280, 20
         sd = make_state_dict(L, E, H, seed=0, qk_gain=qk_gain)
         model = ESM2(L, E, H)
