@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -133,6 +134,16 @@ int gemm_version() {
   return v;
 }
 
+// attention implementation: 2 = attention2.cuh (default), 1 = attention.cuh
+int attn_version() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("ESMB200_ATTN");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -236,7 +247,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
   cudaError_t e;
   {
     ProfScope ps(T_ATTN, st);
-    e = launch_attention(tq, ap, st);
+    e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "attention launch");
   if (probs) {

@@ -161,6 +161,31 @@ def test_attention_forward_and_probs(dev, B, T, H, lengths):
     assert torch.equal(ctx, ctx2)
 
 
+def test_attention_reference_max_raise(dev):
+    """Scores that keep growing along the key axis (each 128-key block beats the previous maximum by far more than
+    the lazy-rescale threshold) force the O-rescale / block-redo path; result must still be the exact softmax."""
+    L = _lib(); lib = L.load()
+    B, T, H = 1, 640, 2
+    E = 64 * H
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = torch.randn(B * T, 3 * E, generator=g)
+    u = torch.randn(64, generator=g)
+    u = u / u.norm() * (8.0 ** 0.5)                              # |u|^2 = 8
+    blk = (torch.arange(T).float() / 128).floor()
+    for h in range(H):
+        qkv[:, h * 64:(h + 1) * 64] = u + 0.1 * torch.randn(T, 64, generator=g)
+        # logits ~ 8 * 0.8 * block index: every block tops the previous maximum by ~6.4 > tau (5.5)
+        qkv[:, E + h * 64:E + (h + 1) * 64] = u * (0.8 * blk[:, None]) + 0.3 * torch.randn(T, 64, generator=g)
+    qkv = qkv.half().to(dev)
+    ctx = torch.empty(B * T, E, dtype=torch.float16, device=dev)
+    probs = torch.empty(B, H, T, T, device=dev)
+    scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
+    L.check(lib.esmb200_attention(P(qkv), None, P(ctx), P(probs), B, T, H, P(scratch), S()))
+    ref_o, ref_p = _attention_ref(qkv, None, B, T, H)
+    torch.testing.assert_close(ctx.float(), ref_o, atol=4e-3, rtol=4e-3)
+    torch.testing.assert_close(probs, ref_p, atol=1e-4, rtol=1e-3)
+
+
 def test_embed_tokens(dev):
     from oracle import esm2_oracle
     from oracle.weights import make_state_dict, make_tokens
