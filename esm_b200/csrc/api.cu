@@ -18,6 +18,7 @@
 
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -134,12 +135,12 @@ int gemm_version() {
   return v;
 }
 
-// attention implementation: 2 = attention2.cuh (default), 1 = attention.cuh
+// attention implementation: 3 = attention3.cuh (default), 2 = attention2.cuh, 1 = attention.cuh
 int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 3;
   }
   return v;
 }
@@ -247,7 +248,14 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
   cudaError_t e;
   {
     ProfScope ps(T_ATTN, st);
-    e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
+    if (attn_version() == 3) {
+      CUtensorMap tkv;
+      rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn3_cfg::BLOCK_KV);
+      if (rc) return rc;
+      e = launch_attention_v3(tq, tkv, ap, st);
+    } else {
+      e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
+    }
   }
   if (e != cudaSuccess) return fail_cuda(e, "attention launch");
   if (probs) {

@@ -83,14 +83,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Blocking wait on phase `parity`. try_wait suspends in hardware for a bounded time, so this is
-// not a hot spin. With the watchdog on, a lost arrival traps after ~4 s instead of hanging the box.
+// Blocking wait on phase `parity`. try_wait suspends in hardware for a bounded time (~100 clk), so this is not a
+// hot spin. With the watchdog on, a lost arrival traps after 2^26 polls (a few seconds) instead of hanging the box;
+// the poll counter costs one integer add + compare per iteration.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
 #if ESMB200_WATCHDOG
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (++polls == (1u << 26)) {
       printf("esmb200: mbarrier watchdog block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();

@@ -76,7 +76,9 @@ def main():
 
     if only and only != "attention":
         print(json.dumps(res)); return
-    qkv = torch.randn(M, 3 * E, device=dev).half()
+    qkv = torch.randn(M, 3 * E, device=dev)
+    qkv[:, :E] *= 0.125  # q is pre-scaled by d^-1/2 in the real pipeline (logits O(1))
+    qkv = qkv.half()
     ctx = torch.empty(M, E, dtype=torch.float16, device=dev)
     scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
     ms = timeit(lambda: L.check(lib.esmb200_attention(P(qkv), None, P(ctx), None, B, T, H, P(scratch), S())))
