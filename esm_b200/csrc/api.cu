@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -135,12 +136,12 @@ int gemm_version() {
   return v;
 }
 
-// attention implementation: 3 = attention3.cuh (default), 2 = attention2.cuh, 1 = attention.cuh
+// attention implementation: 4 = attention4.cuh (persistent, default), 3 / 2 / 1 = earlier kernels kept for A/B runs
 int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 3;
+    v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 4;
   }
   return v;
 }
@@ -174,6 +175,13 @@ int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   ProfScope ps(tag, st);
   cudaError_t e;
   if (tout != nullptr) {
+    static const bool direct = [] { const char* e = getenv("ESMB200_EPI_DIRECT"); return e && e[0] == '1'; }();
+    if (direct && (epi == EPI_QKV_ROPE || epi == EPI_BIAS_GELU)) {
+      e = epi == EPI_QKV_ROPE ? launch_gemm2_epi<EPI_QKV_ROPE, true>(ta, tb, *tout, p, num_sms(), st)
+                              : launch_gemm2_epi<EPI_BIAS_GELU, true>(ta, tb, *tout, p, num_sms(), st);
+      if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");
+      return ESMB200_OK;
+    }
     switch (epi) {
       case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE>(ta, tb, *tout, p, num_sms(), st); break;
       case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL>(ta, tb, *tout, p, num_sms(), st); break;
@@ -248,11 +256,11 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
   cudaError_t e;
   {
     ProfScope ps(T_ATTN, st);
-    if (attn_version() == 3) {
+    if (attn_version() >= 3) {
       CUtensorMap tkv;
       rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn3_cfg::BLOCK_KV);
       if (rc) return rc;
-      e = launch_attention_v3(tq, tkv, ap, st);
+      e = attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st) : launch_attention_v3(tq, tkv, ap, st);
     } else {
       e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
     }

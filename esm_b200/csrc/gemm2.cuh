@@ -47,7 +47,9 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
   }
 }
 
-template <int EPI>
+// DIRECT: fp16 epilogues write their 128-byte row segments straight from registers to global memory instead of
+// staging them in shared memory for a TMA store (keeps the epilogue off the shared-memory bandwidth the mainloop needs)
+template <int EPI, bool DIRECT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -222,17 +224,26 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                                 gelu_erf(__uint_as_float(hi[4 * v + 3]) + bh.w));
             }
           }
-          uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
-          if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
-          named_bar_sync(bar_id, 128);
-          stage_row_sw128(stg, row_local, outv);
-          fence_proxy_async_smem();
-          named_bar_sync(bar_id, 128);
-          if (issuer && row0 < p.M) {  // rows past M are clipped by the tensor map; a fully outside box is skipped
-            tma_store_2d(&tmap_out, stg, col, row0);
-            tma_store_commit();
+          if constexpr (DIRECT) {
+            if (row < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col);
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
+            }
+          } else {
+            uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+            if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
+            named_bar_sync(bar_id, 128);
+            stage_row_sw128(stg, row_local, outv);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (issuer && row0 < p.M) {  // rows past M are clipped by the tensor map; a fully outside box is skipped
+              tma_store_2d(&tmap_out, stg, col, row0);
+              tma_store_commit();
+            }
+            ++store_iter;
           }
-          ++store_iter;
         }
       } else {
 #pragma unroll 1
@@ -284,21 +295,21 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI>
+template <int EPI, bool DIRECT = false>
 inline cudaError_t launch_gemm2_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                                     const GemmParams& p, int num_sms, cudaStream_t stream) {
   using namespace gemm2_cfg;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm2_f16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<EPI, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int tiles = ((p.M + PAIR_M - 1) / PAIR_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_f16_kernel<EPI><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tout, p);
+  gemm2_f16_kernel<EPI, DIRECT><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tout, p);
   return cudaGetLastError();
 }
 
