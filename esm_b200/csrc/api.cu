@@ -20,6 +20,7 @@
 #include "attention2.cuh"
 #include "attention3.cuh"
 #include "attention4.cuh"
+#include "attention5.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -136,12 +137,12 @@ int gemm_version() {
   return v;
 }
 
-// attention implementation: 4 = attention4.cuh (persistent, default), 3 / 2 / 1 = earlier kernels kept for A/B runs
+// attention implementation: 5 = attention5.cuh (persistent + TMEM lookahead, default), 4..1 = earlier kernels (A/B runs)
 int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 4;
+    v = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
   }
   return v;
 }
@@ -260,7 +261,9 @@ int run_attention(const void* qkv, void* ctx, float* probs, const AttnScratch& s
       CUtensorMap tkv;
       rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn3_cfg::BLOCK_KV);
       if (rc) return rc;
-      e = attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st) : launch_attention_v3(tq, tkv, ap, st);
+      e = attn_version() == 5   ? launch_attention_v5(tq, tkv, ap, num_sms(), st)
+          : attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st)
+                                : launch_attention_v3(tq, tkv, ap, st);
     } else {
       e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
     }
