@@ -137,12 +137,13 @@ int gemm_version() {
   return v;
 }
 
-// attention implementation: 5 = attention5.cuh (persistent + TMEM lookahead, default), 4..1 = earlier kernels (A/B runs)
+// attention implementation: 4 = attention4.cuh (persistent, default); 5 = + TMEM lookahead (measured slower);
+// 3 / 2 / 1 = earlier kernels, all kept for A/B runs
 int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 5;
+    v = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 4;
   }
   return v;
 }
@@ -189,6 +190,11 @@ int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUt
       case EPI_BIAS_GELU: e = launch_gemm2_epi<EPI_BIAS_GELU>(ta, tb, *tout, p, num_sms(), st); break;
       case EPI_BIAS_F32: e = launch_gemm2_epi<EPI_BIAS_F32>(ta, tb, *tout, p, num_sms(), st); break;
       case EPI_BIAS_GELU_F32: e = launch_gemm2_epi<EPI_BIAS_GELU_F32>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_NONE: e = launch_gemm2_epi<EPI_NONE>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_LDONLY: e = launch_gemm2_epi<EPI_LDONLY>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_LD_X16: e = launch_gemm2_epi<EPI_LD_X16>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_LD_4WARPS: e = launch_gemm2_epi<EPI_LD_4WARPS>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_LD_BATCH: e = launch_gemm2_epi<EPI_LD_BATCH>(ta, tb, *tout, p, num_sms(), st); break;
       default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
     }
     if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");

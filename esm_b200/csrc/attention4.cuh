@@ -230,9 +230,10 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
           uint32_t sv[2][32];
           tmem_ld_32x32b_x32(ts, sv[0]);
           tmem_ld_32x32b_x32(ts + 32, sv[1]);
-  #pragma unroll
+          tmem_wait_ld_dep(sv[0]);  // ONE tcgen05.wait::ld retires both loads (each extra wait slows the MMA pipe)
+          reg_fence(sv[1]);
+#pragma unroll
           for (int c = 0; c < 2; ++c) {
-            tmem_wait_ld_dep(sv[c]);
             const uint32_t w = kw[c];
             uint32_t pk[16];
             if (w == 0xFFFFFFFFu) {

@@ -29,7 +29,7 @@ constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 320;  // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int STG_BYTES = 128 * 128;  // 128 rows x 128 B staging tile
 constexpr int NUM_STG = 4;            // 2 per 128-column half
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STG * STG_BYTES + 1024 + 256;
@@ -50,7 +50,7 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
 // DIRECT: fp16 epilogues write their 128-byte row segments straight from registers to global memory instead of
 // staging them in shared memory for a TMA store (keeps the epilogue off the shared-memory bandwidth the mainloop needs)
 template <int EPI, bool DIRECT = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using namespace gemm2_cfg;
@@ -95,7 +95,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc_pair(tmem_slot, TMEM_COLS);
     tmem_relinquish_pair();
   }
@@ -147,9 +147,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> regs -> swizzled smem -> TMA store / reduce =====================
-    const uint32_t ew = warp - 4;
+    // 10 warps per CTA (not 12) leave 204 registers per thread: the batched TMEM loads below need 128 of them
+    const uint32_t ew = warp - 2;
     const uint32_t quarter = warp % 4;
     const uint32_t chalf = ew / 4;
     const uint32_t row_local = quarter * 32 + lane;
@@ -170,14 +171,30 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if constexpr (OUT_F16) {
         int t = 0;
         if constexpr (EPI == EPI_QKV_ROPE) t = (row < p.M) ? (row % p.T) : 0;
-#pragma unroll 1
+        // All four 32-column TMEM loads of this warp's 128 columns are issued back to back and retired by ONE
+        // tcgen05.wait::ld: measured on B200 (profiles/r01_epilogue_experiments.txt), every extra ld->wait round
+        // trip in the epilogue slows the concurrently running MMA mainloop (4 waits per tile: -15 %, 1 wait: -0 %).
+        uint32_t acc[4][32];
+        const bool g0_ok = col0 < p.N, g1_ok = col0 + 64 < p.N;  // uniform over the 4 warps of this column half
+        if (g0_ok) {
+          tmem_ld_32x32b_x32(taddr0, acc[0]);
+          tmem_ld_32x32b_x32(taddr0 + 32, acc[1]);
+        }
+        if (g1_ok) {
+          tmem_ld_32x32b_x32(taddr0 + 64, acc[2]);
+          tmem_ld_32x32b_x32(taddr0 + 96, acc[3]);
+        }
+        tmem_wait_ld_dep(acc[0]);
+        reg_fence(acc[1]);
+        reg_fence(acc[2]);
+        reg_fence(acc[3]);
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = col0 + g * 64;
-          if (col >= p.N) break;  // uniform over the 4 warps of this column half
-          uint32_t lo[32], hi[32], outv[32];
-          tmem_ld_32x32b_x32(taddr0 + g * 64, lo);
-          tmem_ld_32x32b_x32(taddr0 + g * 64 + 32, hi);
-          tmem_wait_ld();
+          if (col >= p.N) break;
+          uint32_t (&lo)[32] = acc[2 * g];
+          uint32_t (&hi)[32] = acc[2 * g + 1];
+          uint32_t outv[32];
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           if constexpr (EPI == EPI_QKV_ROPE) {
             const int sect = col / p.E;  // 0 q, 1 k, 2 v
@@ -193,8 +210,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                    __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
               float y1[4], y2[4];
               if (sect < 2) {
-                const float4 c = __ldg(cs4 + j4), s = __ldg(sn4 + j4);
-                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+                const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
+                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float a = x1[e] * sc, b = x2[e] * sc;
@@ -245,14 +262,62 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ++store_iter;
           }
         }
-      } else {
+      } else if constexpr (EPI == EPI_LD_X16) {  // profiling only: 8 loads of 16 columns
+        uint32_t sink = 0;
 #pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t acc[16];
+          tmem_ld_32x32b_x16(taddr0 + c * 16, acc);
+          tmem_wait_ld();
+          sink ^= acc[c];
+        }
+        if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
+      } else if constexpr (EPI == EPI_LD_4WARPS) {  // profiling only: half of the warps read the whole tile
+        uint32_t sink = 0;
+        if (chalf == 0) {
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + c * 32, acc);
+            tmem_wait_ld_dep(acc);
+            sink ^= acc[c];
+          }
+        }
+        if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
+      } else if constexpr (EPI == EPI_LD_BATCH) {  // profiling only: 4 loads in flight, one wait
+        uint32_t a0[32], a1[32], a2[32], a3[32];
+        tmem_ld_32x32b_x32(taddr0, a0);
+        tmem_ld_32x32b_x32(taddr0 + 32, a1);
+        tmem_ld_32x32b_x32(taddr0 + 64, a2);
+        tmem_ld_32x32b_x32(taddr0 + 96, a3);
+        tmem_wait_ld();
+        const uint32_t sink = a0[1] ^ a1[2] ^ a2[3] ^ a3[4];
+        if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
+      } else if constexpr (EPI == EPI_LDONLY) {  // profiling only
+        uint32_t sink = 0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(taddr0 + c * 32, acc);
+          tmem_wait_ld_dep(acc);
+          sink ^= acc[c];
+        }
+        if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
+      } else if constexpr (EPI < EPI_NONE) {
+        // one tcgen05.wait::ld per tile and warp (see the fp16 path)
+        uint32_t acc4[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (col0 + c * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + c * 32, acc4[c]);
+        tmem_wait_ld_dep(acc4[0]);
+        reg_fence(acc4[1]);
+        reg_fence(acc4[2]);
+        reg_fence(acc4[3]);
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int col = col0 + c * 32;
           if (col >= p.N) break;
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(taddr0 + c * 32, acc);
-          tmem_wait_ld();
+          uint32_t (&acc)[32] = acc4[c];
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
@@ -289,7 +354,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }

@@ -71,6 +71,14 @@ def main():
     gemm(L.EPI_QKV_ROPE, 3 * E, E, torch.float16, "gemm_qkv_rope")
     gemm(L.EPI_BIAS_RESIDUAL, E, E, torch.float32, "gemm_out_residual")
     gemm(L.EPI_BIAS_F32, E, E, torch.float32, "gemm_out_plainstore_f32")
+    gemm(5, E, E, torch.float32, "gemm_out_noepilogue")
+    gemm(6, E, E, torch.float32, "gemm_out_tmemld_only")
+    gemm(5, F, E, torch.float32, "gemm_fc1_noepilogue")
+    gemm(6, F, E, torch.float32, "gemm_fc1_tmemld_only")
+    gemm(7, F, E, torch.float32, "gemm_fc1_tmemld_x16")
+    gemm(8, F, E, torch.float32, "gemm_fc1_tmemld_4warps")
+    gemm(9, F, E, torch.float32, "gemm_fc1_tmemld_batch4")
+    gemm(5, E, F, torch.float32, "gemm_fc2_noepilogue")
     gemm(L.EPI_BIAS_GELU, F, E, torch.float16, "gemm_fc1_gelu")
     gemm(L.EPI_BIAS_RESIDUAL, E, F, torch.float32, "gemm_fc2_residual")
 
