@@ -29,7 +29,8 @@ constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 320;  // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int NUM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue (168 regs/thread:
+                                  // 3 warps per SMSP share its 16 K registers)
 constexpr int STG_BYTES = 128 * 128;  // 128 rows x 128 B staging tile
 constexpr int NUM_STG = 4;            // 2 per 128-column half
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STG * STG_BYTES + 1024 + 256;
@@ -47,10 +48,10 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
   }
 }
 
-// DIRECT: fp16 epilogues write their 128-byte row segments straight from registers to global memory instead of
-// staging them in shared memory for a TMA store (keeps the epilogue off the shared-memory bandwidth the mainloop needs)
+// (a variant writing fp16 rows straight from registers to global memory, without smem staging, measured slower:
+// profiles/r01_epilogue_experiments.txt)
 template <int EPI, bool DIRECT = false>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using namespace gemm2_cfg;
@@ -95,7 +96,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 2) {
     tmem_alloc_pair(tmem_slot, TMEM_COLS);
     tmem_relinquish_pair();
   }
@@ -147,10 +148,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> swizzled smem -> TMA store / reduce =====================
-    // 10 warps per CTA (not 12) leave 204 registers per thread: the batched TMEM loads below need 128 of them
-    const uint32_t ew = warp - 2;
+    const uint32_t ew = warp - 4;
     const uint32_t quarter = warp % 4;
     const uint32_t chalf = ew / 4;
     const uint32_t row_local = quarter * 32 + lane;
@@ -168,22 +168,16 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + chalf * 128;
       const int col0 = n_blk * BLOCK_N + chalf * 128;
 
-      if constexpr (OUT_F16) {
-        int t = 0;
-        if constexpr (EPI == EPI_QKV_ROPE) t = (row < p.M) ? (row % p.T) : 0;
+      if constexpr (EPI == EPI_BIAS_GELU) {
         // All four 32-column TMEM loads of this warp's 128 columns are issued back to back and retired by ONE
-        // tcgen05.wait::ld: measured on B200 (profiles/r01_epilogue_experiments.txt), every extra ld->wait round
-        // trip in the epilogue slows the concurrently running MMA mainloop (4 waits per tile: -15 %, 1 wait: -0 %).
+        // tcgen05.wait::ld: measured on B200 (profiles/r01_epilogue_experiments.txt) every extra ld->wait round trip
+        // in the epilogue slows the concurrently running MMA mainloop (4 waits per tile: -15 %, 1 wait: -0 %).
+        // Each 32-column piece is then biased, GELU'd, packed to fp16 and written to the staging tile right away so
+        // that only the 128 accumulator registers stay live.
         uint32_t acc[4][32];
-        const bool g0_ok = col0 < p.N, g1_ok = col0 + 64 < p.N;  // uniform over the 4 warps of this column half
-        if (g0_ok) {
-          tmem_ld_32x32b_x32(taddr0, acc[0]);
-          tmem_ld_32x32b_x32(taddr0 + 32, acc[1]);
-        }
-        if (g1_ok) {
-          tmem_ld_32x32b_x32(taddr0 + 64, acc[2]);
-          tmem_ld_32x32b_x32(taddr0 + 96, acc[3]);
-        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (col0 + c * 32 < p.N) tmem_ld_32x32b_x32(taddr0 + c * 32, acc[c]);
         tmem_wait_ld_dep(acc[0]);
         reg_fence(acc[1]);
         reg_fence(acc[2]);
@@ -191,76 +185,93 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = col0 + g * 64;
-          if (col >= p.N) break;
-          uint32_t (&lo)[32] = acc[2 * g];
-          uint32_t (&hi)[32] = acc[2 * g + 1];
-          uint32_t outv[32];
+          if (col >= p.N) break;  // uniform over the 4 warps of this column half
+          uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+          if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
+          named_bar_sync(bar_id, 128);
+          const uint32_t srow = smem_u32(stg) + row_local * 128;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t (&a)[32] = acc[2 * g + hf];
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col + hf * 32);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {  // 8 columns -> one 16-byte chunk of the 128-byte staging row
+              const float4 b0 = __ldg(b4 + 2 * v), b1 = __ldg(b4 + 2 * v + 1);
+              const uint32_t o0 = pack_half2(gelu_erf(__uint_as_float(a[8 * v + 0]) + b0.x),
+                                             gelu_erf(__uint_as_float(a[8 * v + 1]) + b0.y));
+              const uint32_t o1 = pack_half2(gelu_erf(__uint_as_float(a[8 * v + 2]) + b0.z),
+                                             gelu_erf(__uint_as_float(a[8 * v + 3]) + b0.w));
+              const uint32_t o2 = pack_half2(gelu_erf(__uint_as_float(a[8 * v + 4]) + b1.x),
+                                             gelu_erf(__uint_as_float(a[8 * v + 5]) + b1.y));
+              const uint32_t o3 = pack_half2(gelu_erf(__uint_as_float(a[8 * v + 6]) + b1.z),
+                                             gelu_erf(__uint_as_float(a[8 * v + 7]) + b1.w));
+              const uint32_t chunk = (uint32_t)(hf * 4 + v);
+              const uint32_t addr = srow + ((chunk ^ (row_local & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer && row0 < p.M) {  // rows past M are clipped by the tensor map; a fully outside box is skipped
+            tma_store_2d(&tmap_out, stg, col, row0);
+            tma_store_commit();
+          }
+          ++store_iter;
+        }
+      } else if constexpr (EPI == EPI_QKV_ROPE) {
+        const int t = (row < p.M) ? (row % p.T) : 0;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + g * 64;
+          if (col >= p.N) break;  // uniform over the 4 warps of this column half
+          uint32_t lo[32], hi[32], outv[32];
+          tmem_ld_32x32b_x32(taddr0 + g * 64, lo);
+          tmem_ld_32x32b_x32(taddr0 + g * 64 + 32, hi);
+          tmem_wait_ld_dep(lo);  // one wait retires both loads
+          reg_fence(hi);
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-          if constexpr (EPI == EPI_QKV_ROPE) {
-            const int sect = col / p.E;  // 0 q, 1 k, 2 v
-            const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
-            const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
-            const float sc = (sect == 0) ? p.q_scale : 1.0f;
+          const int sect = col / p.E;  // 0 q, 1 k, 2 v
+          const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
+          const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
+          const float sc = (sect == 0) ? p.q_scale : 1.0f;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
-              const float x1[4] = {__uint_as_float(lo[4 * j4 + 0]) + bl.x, __uint_as_float(lo[4 * j4 + 1]) + bl.y,
-                                   __uint_as_float(lo[4 * j4 + 2]) + bl.z, __uint_as_float(lo[4 * j4 + 3]) + bl.w};
-              const float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
-                                   __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
-              float y1[4], y2[4];
-              if (sect < 2) {
-                const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
-                const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
+            const float x1[4] = {__uint_as_float(lo[4 * j4 + 0]) + bl.x, __uint_as_float(lo[4 * j4 + 1]) + bl.y,
+                                 __uint_as_float(lo[4 * j4 + 2]) + bl.z, __uint_as_float(lo[4 * j4 + 3]) + bl.w};
+            const float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
+                                 __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
+            float y1[4], y2[4];
+            if (sect < 2) {
+              const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
+              const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a = x1[e] * sc, b = x2[e] * sc;
-                  y1[e] = a * cc[e] - b * ss[e];
-                  y2[e] = b * cc[e] + a * ss[e];
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { y1[e] = x1[e]; y2[e] = x2[e]; }
+              for (int e = 0; e < 4; ++e) {
+                const float a = x1[e] * sc, b = x2[e] * sc;
+                y1[e] = a * cc[e] - b * ss[e];  // rotary_embedding.py:16-20 with rotate_half = cat(-x2, x1)
+                y2[e] = b * cc[e] + a * ss[e];
               }
-              outv[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
-              outv[2 * j4 + 1] = pack_half2(y1[2], y1[3]);
-              outv[16 + 2 * j4 + 0] = pack_half2(y2[0], y2[1]);
-              outv[16 + 2 * j4 + 1] = pack_half2(y2[2], y2[3]);
-            }
-          } else {  // EPI_BIAS_GELU
+            } else {
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 bl = __ldg(b4 + v), bh = __ldg(b4 + 8 + v);
-              outv[2 * v] = pack_half2(gelu_erf(__uint_as_float(lo[4 * v + 0]) + bl.x),
-                                       gelu_erf(__uint_as_float(lo[4 * v + 1]) + bl.y));
-              outv[2 * v + 1] = pack_half2(gelu_erf(__uint_as_float(lo[4 * v + 2]) + bl.z),
-                                           gelu_erf(__uint_as_float(lo[4 * v + 3]) + bl.w));
-              outv[16 + 2 * v] = pack_half2(gelu_erf(__uint_as_float(hi[4 * v + 0]) + bh.x),
-                                            gelu_erf(__uint_as_float(hi[4 * v + 1]) + bh.y));
-              outv[16 + 2 * v + 1] = pack_half2(gelu_erf(__uint_as_float(hi[4 * v + 2]) + bh.z),
-                                                gelu_erf(__uint_as_float(hi[4 * v + 3]) + bh.w));
+              for (int e = 0; e < 4; ++e) { y1[e] = x1[e]; y2[e] = x2[e]; }
             }
+            outv[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
+            outv[2 * j4 + 1] = pack_half2(y1[2], y1[3]);
+            outv[16 + 2 * j4 + 0] = pack_half2(y2[0], y2[1]);
+            outv[16 + 2 * j4 + 1] = pack_half2(y2[2], y2[3]);
           }
-          if constexpr (DIRECT) {
-            if (row < p.M) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col);
-#pragma unroll
-              for (int v = 0; v < 8; ++v)
-                dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
-            }
-          } else {
-            uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
-            if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
-            named_bar_sync(bar_id, 128);
-            stage_row_sw128(stg, row_local, outv);
-            fence_proxy_async_smem();
-            named_bar_sync(bar_id, 128);
-            if (issuer && row0 < p.M) {  // rows past M are clipped by the tensor map; a fully outside box is skipped
-              tma_store_2d(&tmap_out, stg, col, row0);
-              tma_store_commit();
-            }
-            ++store_iter;
+          uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+          if (issuer) tma_store_wait_read<1>();
+          named_bar_sync(bar_id, 128);
+          stage_row_sw128(stg, row_local, outv);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer && row0 < p.M) {
+            tma_store_2d(&tmap_out, stg, col, row0);
+            tma_store_commit();
           }
+          ++store_iter;
         }
       } else if constexpr (EPI == EPI_LD_X16) {  // profiling only: 8 loads of 16 columns
         uint32_t sink = 0;
@@ -354,7 +365,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 0) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
