@@ -300,8 +300,13 @@ def main():
             ach, peak, unit = amount / avg / 1e9, peaks["tensor_sustained"], "TFLOP/s"
         else:
             ach, peak, unit = amount / avg / 1e6, peaks["hbm"], "GB/s"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes per token of this kernel from a committed ncu --set full capture
+            bpt = json.load(open(tpath))["bytes_per_token"].get(dom)
+            traffic = round(bpt * M) if bpt else None
         roofline = {"kernel": dom, "bound": kind, "achieved": round(ach, 1), "peak": peak, "unit": unit,
-                    "frac": round(ach / peak, 4), "traffic": None,
+                    "frac": round(ach / peak, 4), "traffic": traffic,
                     "peak_source": peaks["source"] + (", sustained (kernel timed inside a long step)" if kind == "tensor" else ""),
                     "avg_launch_ms": round(avg, 4), "algorithmic_per_launch": amount}
 

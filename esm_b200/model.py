@@ -201,7 +201,13 @@ def gelu(x):
 
 
 class RobertaLMHead(nn.Module):
-    """modules.py:298-314 — kept in PyTorch fp32 (0.23 % of the FLOPs; SURVEY §8f #2 lists it as a next row)."""
+    """modules.py:298-314: dense -> gelu -> LayerNorm -> tied-embedding projection + bias.
+
+    `forward(features)` is the plain PyTorch evaluation (used on already layer-normed features, e.g. by callers that
+    hold a representation).  `forward_native(x_pre_ln, ln_w, ln_b, eps)` is what ESM2.forward uses on the GPU: it
+    starts from the residual stream BEFORE emb_layer_norm_after and runs the whole tail through libesmb200.so
+    (LayerNorm->fp16 | tcgen05 GEMM + bias + erf-GELU | LayerNorm->fp16 | tcgen05 GEMM onto the 33 tokens, padded to 64
+    output columns), replacing ~25 ms of fp32 cuBLAS + elementwise passes per 256x1024-token batch by ~2 ms."""
 
     def __init__(self, embed_dim, output_dim, weight):
         super().__init__()
@@ -209,12 +215,48 @@ class RobertaLMHead(nn.Module):
         self.layer_norm = nn.LayerNorm(embed_dim)
         self.weight = weight
         self.bias = nn.Parameter(torch.zeros(output_dim))
+        self._packed = None
+        self._packed_key = None
 
     def forward(self, features):
         x = self.dense(features)
         x = gelu(x)
         x = self.layer_norm(x)
         return F.linear(x, self.weight) + self.bias
+
+    def _pack(self):
+        ps = [self.dense.weight, self.weight, self.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or key != self._packed_key:
+            E = self.dense.weight.shape[1]
+            V = self.weight.shape[0]
+            npad = (V + 63) // 64 * 64  # GEMM N must be a multiple of 64
+            w_out = torch.zeros((npad, E), dtype=torch.float16, device=self.weight.device)
+            w_out[:V] = self.weight.detach().half()
+            b_out = torch.zeros((npad,), dtype=torch.float32, device=self.weight.device)
+            b_out[:V] = self.bias.detach().float()
+            self._packed = (self.dense.weight.detach().half().contiguous(), w_out, b_out, V, npad)
+            self._packed_key = key
+        return self._packed
+
+    def forward_native(self, x_pre: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float) -> torch.Tensor:
+        """x_pre: fp32 [B,T,E] residual stream before emb_layer_norm_after (esm2.py:123). Returns logits [B,T,V]."""
+        lib = _lib.load()
+        B, T, E = x_pre.shape
+        M = B * T
+        dev = x_pre.device
+        w_dense, w_out, b_out, V, npad = self._pack()
+        a16 = torch.empty((M, E), dtype=torch.float16, device=dev)
+        _lib.check(lib.esmb200_layernorm_f16(_ptr(x_pre), _ptr(ln_w), _ptr(ln_b), _ptr(a16), M, E, eps, _stream()))
+        h = torch.empty((M, E), dtype=torch.float32, device=dev)
+        _lib.check(lib.esmb200_gemm_f16(_lib.EPI_BIAS_GELU_F32, _ptr(a16), _ptr(w_dense), _ptr(self.dense.bias),
+                                        _ptr(h), M, E, E, None, None, 0, 0, _stream()))
+        _lib.check(lib.esmb200_layernorm_f16(_ptr(h), _ptr(self.layer_norm.weight), _ptr(self.layer_norm.bias),
+                                             _ptr(a16), M, E, self.layer_norm.eps, _stream()))
+        logits = torch.empty((M, npad), dtype=torch.float32, device=dev)
+        _lib.check(lib.esmb200_gemm_f16(_lib.EPI_BIAS_F32, _ptr(a16), _ptr(w_out), _ptr(b_out), _ptr(logits), M, npad, E,
+                                        None, None, 0, 0, _stream()))
+        return logits.view(B, T, npad)[:, :, :V]
 
 
 class ContactPredictionHead(nn.Module):
@@ -319,13 +361,14 @@ class ESM2(nn.Module):
             attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out, list(range(N)) if need_head_weights else [])
             for i, t in repr_out.items():
                 hidden[i + 1] = t
+            # esm2.py:129 LM head, from the pre-LN stream (its first step is the same emb_layer_norm_after)
+            ln = self.emb_layer_norm_after
+            logits = self.lm_head.forward_native(x, ln.weight, ln.bias, ln.eps)
             # esm2.py:123-128 final LayerNorm; the last representation is post-LN
-            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(self.emb_layer_norm_after.weight),
-                                             _ptr(self.emb_layer_norm_after.bias), _ptr(x), B * T, E,
-                                             self.emb_layer_norm_after.eps, _stream()))
+            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(ln.weight), _ptr(ln.bias), _ptr(x), B * T, E, ln.eps,
+                                             _stream()))
         if N in repr_layers:
             hidden[N] = x
-        logits = self.lm_head(x)
         result = {"logits": logits, "representations": hidden}
         if need_head_weights:
             attentions = torch.stack([attn_t[i] for i in range(N)], 1)  # B x L x H x T x T (esm2.py:134)
