@@ -182,6 +182,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # no NCCL version banner on stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from esm_b200 import _lib, pretrained
