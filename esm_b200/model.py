@@ -354,7 +354,11 @@ class ESM2(nn.Module):
                                                 self.padding_idx, self.mask_idx, int(self.token_dropout), _stream()))
             if 0 in repr_layers:
                 hidden[0] = x.clone()
-            mask = padding_mask if bool(padding_mask.any()) else None  # esm2.py:108-109
+            # esm2.py:108-109 drops the mask when the batch has no padding; that test is a device->host sync, which
+            # would serialise back-to-back forwards (bulk extraction). The kernels take the all-false mask at no cost
+            # (one uniform compare per 32 keys), so the mask is always passed and the sync is only paid on the
+            # need_head_weights path below, where the reference's result depends on it.
+            mask = padding_mask
             # esm2.py:111-121 layer loop (intermediate representations are copied out by the library)
             repr_out = {i - 1: torch.empty_like(x) for i in repr_layers if 0 < i < N}
             cos, sin = self._rope_tables(T)
@@ -372,7 +376,7 @@ class ESM2(nn.Module):
         result = {"logits": logits, "representations": hidden}
         if need_head_weights:
             attentions = torch.stack([attn_t[i] for i in range(N)], 1)  # B x L x H x T x T (esm2.py:134)
-            if mask is not None:
+            if bool(padding_mask.any()):  # esm2.py:135-139
                 am = 1 - mask.type_as(attentions)
                 am = am.unsqueeze(1) * am.unsqueeze(2)
                 attentions = attentions * am[:, None, None, :, :]

@@ -78,6 +78,8 @@ def main():
     gemm(7, F, E, torch.float32, "gemm_fc1_tmemld_x16")
     gemm(8, F, E, torch.float32, "gemm_fc1_tmemld_4warps")
     gemm(9, F, E, torch.float32, "gemm_fc1_tmemld_batch4")
+    gemm(10, F, E, torch.float16, "gemm_fc1_gelu_mathonly")
+    gemm(11, F, E, torch.float16, "gemm_fc1_f16_storeonly")
     gemm(5, E, F, torch.float32, "gemm_fc2_noepilogue")
     gemm(L.EPI_BIAS_GELU, F, E, torch.float16, "gemm_fc1_gelu")
     gemm(L.EPI_BIAS_RESIDUAL, E, F, torch.float32, "gemm_fc2_residual")

@@ -108,3 +108,75 @@ def test_full_size_properties_650M():
     assert torch.equal(alone[0], out[1, :702])
     row_mean = out[0].mean(-1).abs().max()
     assert float(row_mean) < 1.0
+
+
+def test_3B_width_contacts():
+    """BASELINE.json configs[3] width (E=2560, H=40, F=10240; 2 of the 36 layers), need_head_weights / contacts path,
+    ragged batch, T=260 (3 key blocks of 128 for the probability kernel, 5 blocks of 64 for the forward kernel)."""
+    from oracle import esm2_oracle
+    from oracle.weights import make_tokens
+    L, E, H = 2, 2560, 40
+    model, sd = build_model(L, E, H)
+    tokens = make_tokens([258, 100], 260, seed=3, n_mask=1)
+    ref = esm2_oracle.esm2_forward(sd, L, H, tokens, repr_layers=[1, 2], return_contacts=True)
+    out = model(tokens.cuda(), repr_layers=[1, 2], return_contacts=True)
+    for k in (1, 2):
+        assert rel_fro(out["representations"][k].cpu(), ref["representations"][k]) <= REL_FRO
+    assert rel_fro(out["logits"].cpu(), ref["logits"]) <= REL_FRO_LOGITS
+    assert out["attentions"].shape == (2, L, H, 260, 260)
+    assert float((out["attentions"].cpu() - ref["attentions"]).abs().max()) <= ATT_ABS
+    assert float((out["contacts"].cpu() - ref["contacts"]).abs().max()) <= CONTACT_ABS
+
+
+def test_bulk_embedder_host_to_host():
+    """esm_b200.extract.BulkEmbedder (the e2e call bench.py times): pinned host tokens in, host mean / bos / per-token
+    representations out, micro-batched with copy/compute overlap — must equal one direct forward."""
+    from esm_b200.extract import BulkEmbedder
+    from oracle.weights import make_tokens
+    model, _ = build_model(2, 128, 2)
+    tokens = make_tokens([60, 33, 47, 12, 60, 5, 29], 62, seed=9)
+    direct = model(tokens.cuda(), repr_layers=[2])["representations"][2].cpu()
+    emb = BulkEmbedder(model, include=("mean", "bos", "per_tok"), micro_batch=3)
+    res = emb.embed(tokens.pin_memory())
+    assert torch.equal(res["per_tok"], direct)
+    assert torch.equal(res["bos"], direct[:, 0])
+    lengths = [60, 33, 47, 12, 60, 5, 29]
+    for i, n in enumerate(lengths):
+        torch.testing.assert_close(res["mean"][i], direct[i, 1:n + 1].mean(0), atol=1e-5, rtol=1e-5)
+    assert emb.d2h_bytes == res["per_tok"].numel() * 4 + 2 * res["mean"].numel() * 4
+
+
+def test_extract_cli_writes_reference_schema(tmp_path):
+    """python -m esm_b200.extract_cli: files and keys of scripts/extract.py:104-131, values against the oracle."""
+    import argparse
+    from esm_b200 import extract_cli, pretrained
+    from oracle import esm2_oracle
+    from oracle.weights import make_state_dict
+    from esm_b200 import ESM2
+    L, E, H = 2, 128, 2
+    sd = make_state_dict(L, E, H)
+    ckpt = tmp_path / "esm2_tiny.pt"
+    torch.save({"cfg": {"model": {"encoder_layers": L, "encoder_embed_dim": E, "encoder_attention_heads": H,
+                                  "token_dropout": True}},
+                "model": {("encoder.sentence_encoder." + k): v for k, v in sd.items()}}, ckpt)
+    fasta = tmp_path / "in.fasta"
+    seqs = {"p1": "MKTVRQERLKSIVRILERSKEPVSGAQ", "p2": "KALTARQQEVFDLIRD", "p3": "MKT"}
+    fasta.write_text("".join(f">{k}\n{v}\n" for k, v in seqs.items()))
+    outdir = tmp_path / "out"
+    args = argparse.Namespace(model_location=str(ckpt), fasta_file=fasta, output_dir=outdir, toks_per_batch=64,
+                              repr_layers=[-1], include=["mean", "per_tok", "bos", "contacts"],
+                              truncation_seq_length=1022)
+    n = extract_cli.run(args)
+    assert n == 3
+    model, alphabet = pretrained.load_model_and_alphabet(str(ckpt))
+    for label, seq in seqs.items():
+        r = torch.load(outdir / f"{label}.pt", weights_only=False)
+        assert set(r.keys()) == {"label", "representations", "mean_representations", "bos_representations", "contacts"}
+        _, _, tok = alphabet.get_batch_converter()([(label, seq)])
+        ref = esm2_oracle.esm2_forward(sd, L, H, tok, repr_layers=[L], return_contacts=True)
+        want = ref["representations"][L][0, 1:len(seq) + 1]
+        assert r["representations"][L].shape == (len(seq), E)
+        assert rel_fro(r["representations"][L], want) <= REL_FRO
+        assert rel_fro(r["mean_representations"][L], want.mean(0)) <= REL_FRO
+        assert r["contacts"].shape == (len(seq), len(seq))
+        assert float((r["contacts"] - ref["contacts"][0]).abs().max()) <= CONTACT_ABS
