@@ -267,7 +267,8 @@ struct ProbsParams {
   int words;
   const float* row_max;
   const float* row_sum;
-  float* probs;  // [B,H,T,T]
+  float* probs;  // [B,H,T,T], batch b starting at probs + b * batch_stride (elements)
+  long long batch_stride;
 };
 
 namespace probs_cfg {
@@ -327,7 +328,7 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
   const uint32_t quarter = warp % 4;
   const int t = q0 + quarter * 32 + lane;
   const bool row_ok = t < p.T;
-  float* dst = p.probs + (((size_t)b * p.H + h) * p.T + (row_ok ? t : 0)) * p.T + k0;
+  float* dst = p.probs + (size_t)b * p.batch_stride + ((size_t)h * p.T + (row_ok ? t : 0)) * p.T + k0;
   const int ncols = min(BLOCK_KV, p.T - k0);  // multiple of 4 is NOT guaranteed -> scalar tail below
   if (live) {
     const size_t si = ((size_t)b * p.H + h) * p.T + (row_ok ? t : 0);

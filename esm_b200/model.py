@@ -140,7 +140,7 @@ class TransformerLayer(nn.Module):
         attn = run_stack([self], xb, self_attn_padding_mask, cos, sin, None, [0] if need_head_weights else [])
         out = xb.transpose(0, 1).to(x.dtype)
         if need_head_weights:
-            return out, attn[0].transpose(0, 1)  # (B,H,T,T) -> (H,B,T,T), multihead_attention.py:398-400
+            return out, attn[0].transpose(0, 1).contiguous()  # (B,H,T,T) -> (H,B,T,T), multihead_attention.py:398-400
         return out, None
 
 
@@ -184,14 +184,21 @@ def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask:
                 reprs[i] = t.data_ptr()
         attns = (ctypes.c_void_p * n)()
         attn_t = {}
-        for i in attn_layers:
-            a = torch.empty((B, H, T, T), dtype=torch.float32, device=x.device)
-            attn_t[i] = a
-            attns[i] = a.data_ptr()
+        stacked = None
+        if attn_layers:
+            # one [B, n_attn, H, T, T] allocation, layer i written straight into its slice (esm2.py:134's stack)
+            stacked = torch.empty((B, len(attn_layers), H, T, T), dtype=torch.float32, device=x.device)
+            for pos, i in enumerate(attn_layers):
+                a = stacked[:, pos]
+                attn_t[i] = a
+                attns[i] = a.data_ptr()
         keep.append(mask)
         _lib.check(lib.esmb200_stack_forward(handles, n, _ptr(x), _ptr(mask), B, T, _ptr(rope_cos), _ptr(rope_sin),
                                              reprs if repr_out else None, attns if attn_layers else None,
+                                             (len(attn_layers) * H * T * T) if attn_layers else 0,
                                              _ptr(ws), ws.numel(), _stream()))
+    if stacked is not None:
+        attn_t["stacked"] = stacked
     return attn_t
 
 
@@ -274,24 +281,33 @@ class ContactPredictionHead(nn.Module):
         self.activation = nn.Sigmoid()
 
     def forward(self, tokens, attentions):
+        """modules.py:338-357 evaluated without the [B, L*H, S, S] temporaries of symmetrize/apc (which need ~6x the
+        24 GB attention stack of configs[3]): with A_c the eos-masked, cropped map of channel c = (layer, head),
+            logit_ij = sum_c w_c (A_c + A_c^T)_ij - sum_c (w_c / a12_c) a1_c[i] a1_c[j] + b,
+            a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum(a1_c),
+        accumulated layer by layer: a weighted sum over heads and a rank-H outer product per layer."""
+        B, L, H, T, _ = attentions.shape
+        lo = 1 if self.prepend_bos else 0
+        hi = T - 1 if self.append_eos else T
+        S = hi - lo
+        w = self.regression.weight.view(L, H).to(attentions.dtype)
+        keep = None
         if self.append_eos:
-            eos_mask = tokens.ne(self.eos_idx).to(attentions)
-            eos_mask = eos_mask.unsqueeze(1) * eos_mask.unsqueeze(2)
-            attentions = attentions * eos_mask[:, None, None, :, :]
-            attentions = attentions[..., :-1, :-1]
-        if self.prepend_bos:
-            attentions = attentions[..., 1:, 1:]
-        batch_size, layers, heads, seqlen, _ = attentions.size()
-        attentions = attentions.reshape(batch_size, layers * heads, seqlen, seqlen)
-        attentions = attentions.to(self.regression.weight.device)
-        x = attentions + attentions.transpose(-1, -2)
-        a1 = x.sum(-1, keepdims=True)
-        a2 = x.sum(-2, keepdims=True)
-        a12 = x.sum((-1, -2), keepdims=True)
-        avg = a1 * a2
-        avg.div_(a12)
-        x = (x - avg).permute(0, 2, 3, 1)
-        return self.activation(self.regression(x).squeeze(3))
+            keep = tokens.ne(self.eos_idx).to(attentions)[:, lo:hi]  # [B,S]
+        acc = torch.zeros((B, S, S), dtype=attentions.dtype, device=attentions.device)
+        corr = torch.zeros_like(acc)
+        for l in range(L):
+            a = attentions[:, l, :, lo:hi, lo:hi]  # [B,H,S,S] view
+            if keep is not None:
+                a = a * (keep[:, None, :, None] * keep[:, None, None, :])
+            acc += torch.einsum("bhij,h->bij", a, w[l])
+            a1 = a.sum(-1) + a.sum(-2)  # [B,H,S]
+            a12 = a1.sum(-1)            # [B,H]
+            corr += torch.einsum("bhi,bhj->bij", a1 * (w[l][None, :] / a12)[:, :, None], a1)
+        logits = acc + acc.transpose(-1, -2) - corr
+        if self.regression.bias is not None:
+            logits = logits + self.regression.bias
+        return self.activation(logits)
 
 
 class ESM2(nn.Module):
@@ -375,11 +391,11 @@ class ESM2(nn.Module):
             hidden[N] = x
         result = {"logits": logits, "representations": hidden}
         if need_head_weights:
-            attentions = torch.stack([attn_t[i] for i in range(N)], 1)  # B x L x H x T x T (esm2.py:134)
-            if bool(padding_mask.any()):  # esm2.py:135-139
+            attentions = attn_t["stacked"]  # B x L x H x T x T (esm2.py:134), written in place by the library
+            if bool(padding_mask.any()):  # esm2.py:135-139 (in place: the tensor is ours)
                 am = 1 - mask.type_as(attentions)
                 am = am.unsqueeze(1) * am.unsqueeze(2)
-                attentions = attentions * am[:, None, None, :, :]
+                attentions.mul_(am[:, None, None, :, :])
             result["attentions"] = attentions
             if return_contacts:
                 result["contacts"] = self.contact_head(tokens, attentions)
