@@ -89,7 +89,8 @@ def _declare(lib):
                                           c_void_p, c_void_p, c_size_t, c_void_p]
     lib.esmb200_stack_forward.restype = c_int32
     lib.esmb200_stack_forward.argtypes = [POINTER(c_void_p), c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
-                                          c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_void_p, c_size_t, c_void_p]
+                                          c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int32, c_void_p, c_size_t,
+                                          c_void_p]
     lib.esmb200_embed_tokens.restype = c_int32
     lib.esmb200_embed_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_void_p]

@@ -250,8 +250,8 @@ int run_key_bits(const uint8_t* pad_mask, const AttnScratch& s, int B, int T, cu
   return ESMB200_OK;
 }
 
-int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batch_stride, const AttnScratch& s, int B,
-                  int T, int H, cudaStream_t st) {
+int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batch_stride, int attn_flags,
+                  const AttnScratch& s, int B, int T, int H, cudaStream_t st) {
   const int E = H * 64;
   CUtensorMap tq;
   int rc = make_tmap_f16(&tq, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, 128);
@@ -284,6 +284,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
     pp.keybits = s.keybits; pp.kvlen = s.kvlen; pp.words = s.words;
     pp.row_max = s.row_max; pp.row_sum = s.row_sum; pp.probs = probs;
     pp.batch_stride = probs_batch_stride > 0 ? probs_batch_stride : (long long)H * T * T;
+    pp.zero_pad_rows = attn_flags & 1;
     {
       ProfScope ps(T_PROBS, st);
       e = launch_attention_probs(tq, pp, st);
@@ -439,8 +440,8 @@ struct ActMaps {
 };
 
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
-                       float* attn_probs, long long attn_batch_stride, const Workspace& ws, const ActMaps& am,
-                       cudaStream_t st) {
+                       float* attn_probs, long long attn_batch_stride, int attn_flags, const Workspace& ws,
+                       const ActMaps& am, cudaStream_t st) {
   const int E = L->E, F = L->F, H = L->H;
   const int M = B * T;
   cudaError_t e;
@@ -458,7 +459,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
-  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, ws.as, B, T, H, st);
+  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st);
   if (rc) return rc;
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
@@ -496,8 +497,8 @@ int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int F
 
 int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float* x, const uint8_t* pad_mask,
                           int32_t B, int32_t T, const float* rope_cos, const float* rope_sin,
-                          float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride,
+                          int32_t attn_flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (!layers || n_layers <= 0 || !x || !rope_cos || !rope_sin || !workspace)
     return fail(ESMB200_EINVAL, "null argument");
   if (B <= 0 || T <= 0) return fail(ESMB200_EINVAL, "empty batch");
@@ -518,7 +519,7 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   if (rc) return rc;
   for (int i = 0; i < n_layers; ++i) {
     rc = layer_forward_impl(layers[i], x, B, T, rope_cos, rope_sin, attn_out ? attn_out[i] : nullptr, attn_batch_stride,
-                            ws, am, st);
+                            attn_flags, ws, am, st);
     if (rc) return rc;
     if (repr_out && repr_out[i])
       CK(cudaMemcpyAsync(repr_out[i], x, (size_t)B * T * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -533,7 +534,7 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
   float* attn_arr[1] = {attn_probs};
   esmb200_layer* arr[1] = {layer};
   return esmb200_stack_forward(arr, 1, x, pad_mask, B, T, rope_cos, rope_sin, nullptr, attn_probs ? attn_arr : nullptr,
-                               0, workspace, workspace_bytes, stream);
+                               0, 0, workspace, workspace_bytes, stream);
 }
 
 int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, int32_t B, int32_t T, int32_t E,
@@ -600,7 +601,7 @@ int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float
   AttnScratch s = carve_attn_scratch(scratch, B, T, H);
   rc = run_key_bits(pad_mask, s, B, T, st);
   if (rc) return rc;
-  return run_attention(qkv, ctx, attn_probs, 0, s, B, T, H, st);
+  return run_attention(qkv, ctx, attn_probs, 0, 0, s, B, T, H, st);
 }
 
 

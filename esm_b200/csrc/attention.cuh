@@ -269,12 +269,13 @@ struct ProbsParams {
   const float* row_sum;
   float* probs;  // [B,H,T,T], batch b starting at probs + b * batch_stride (elements)
   long long batch_stride;
+  int zero_pad_rows;  // 1: rows of padded query tokens are written as zeros (ESM2.forward's stacked result)
 };
 
 namespace probs_cfg {
 constexpr int NUM_THREADS = 128;
 constexpr int TMEM_COLS = 128;
-constexpr int SMEM_BYTES = 2 * attn_cfg::TILE_BYTES + 1024 + 64;
+constexpr int SMEM_BYTES = 2 * attn_cfg::TILE_BYTES + 1024 + 64 + 4 * 32 * 33 * 4;  // + per-warp transpose tiles
 }  // namespace probs_cfg
 
 __global__ void __launch_bounds__(probs_cfg::NUM_THREADS, 4)
@@ -325,36 +326,51 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
   }
   __syncwarp();
 
+  // Each thread owns one query row in TMEM; the 32x32 fp32 piece of a warp is transposed through padded shared
+  // memory so that every global store instruction writes one 128-byte row segment (lane = key column).
   const uint32_t quarter = warp % 4;
-  const int t = q0 + quarter * 32 + lane;
+  const int t_warp0 = q0 + quarter * 32;       // first query row of this warp
+  const int t = t_warp0 + lane;
   const bool row_ok = t < p.T;
-  float* dst = p.probs + (size_t)b * p.batch_stride + ((size_t)h * p.T + (row_ok ? t : 0)) * p.T + k0;
-  const int ncols = min(BLOCK_KV, p.T - k0);  // multiple of 4 is NOT guaranteed -> scalar tail below
+  const int ncols = min(BLOCK_KV, p.T - k0);
+  float* tile = reinterpret_cast<float*>(smem + 2 * TILE_BYTES + 64) + warp * (32 * 33);
+  float* base = p.probs + (size_t)b * p.batch_stride + (size_t)h * p.T * p.T + k0;
+  float mneg = 0.f, inv = 0.f;
+  uint32_t kw[4] = {0u, 0u, 0u, 0u};
   if (live) {
     const size_t si = ((size_t)b * p.H + h) * p.T + (row_ok ? t : 0);
-    const float mneg = -p.row_max[si] * LOG2E;
+    mneg = -p.row_max[si] * LOG2E;
     const float l = p.row_sum[si];
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    inv = l > 0.f ? 1.0f / l : 0.f;
+    // esm2.py:135-139: rows of padded QUERY tokens are zero in the stacked result (padded key columns already are)
+    if (p.zero_pad_rows && row_ok && !((p.keybits[(size_t)b * p.words + (t >> 5)] >> (t & 31)) & 1u)) inv = 0.f;
     const uint4 kw4 = __ldg(reinterpret_cast<const uint4*>(p.keybits + (size_t)b * p.words + kb * 4));
-    const uint32_t kw[4] = {kw4.x, kw4.y, kw4.z, kw4.w};
+    kw[0] = kw4.x; kw[1] = kw4.y; kw[2] = kw4.z; kw[3] = kw4.w;
     mbar_wait(mma_done, 0);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    if (c * 32 >= ncols) break;
+    if (live) {
       uint32_t sv[32];
       tmem_ld_32x32b_x32(tmem_s + ((quarter * 32u) << 16) + c * 32, sv);
-      tmem_wait_ld();
+      tmem_wait_ld_dep(sv);
       const uint32_t w = kw[c];
-      if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = ((w >> i) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, mneg)) * inv : 0.f;
-          if (c * 32 + i < ncols) dst[c * 32 + i] = pr;
-        }
-      }
+      for (int i = 0; i < 32; ++i)
+        tile[lane * 33 + i] = ((w >> i) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, mneg)) * inv : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = 0.f;
     }
-  } else if (row_ok) {
-    for (int i = 0; i < ncols; ++i) dst[i] = 0.f;
+    __syncwarp();
+    const int col = c * 32 + lane;
+    if (col < ncols) {
+      const int nrows = min(32, p.T - t_warp0);
+      for (int r = 0; r < nrows; ++r) base[(size_t)(t_warp0 + r) * p.T + col] = tile[r * 33 + lane];
+    }
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -158,7 +158,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask: Optional[torch.Tensor],
               rope_cos: torch.Tensor, rope_sin: torch.Tensor, repr_out: Optional[Dict[int, torch.Tensor]],
-              attn_layers: Sequence[int]):
+              attn_layers: Sequence[int], zero_pad_rows: bool = False):
     """esmb200_stack_forward on x fp32 (B,T,E) in place. repr_out: {layer index (0-based): (B,T,E) tensor to fill}.
     Returns {layer index: (B,H,T,T) fp32} for the indices in attn_layers."""
     if not x.is_cuda:
@@ -196,6 +196,7 @@ def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask:
         _lib.check(lib.esmb200_stack_forward(handles, n, _ptr(x), _ptr(mask), B, T, _ptr(rope_cos), _ptr(rope_sin),
                                              reprs if repr_out else None, attns if attn_layers else None,
                                              (len(attn_layers) * H * T * T) if attn_layers else 0,
+                                             1 if zero_pad_rows else 0,
                                              _ptr(ws), ws.numel(), _stream()))
     if stacked is not None:
         attn_t["stacked"] = stacked
@@ -378,7 +379,8 @@ class ESM2(nn.Module):
             # esm2.py:111-121 layer loop (intermediate representations are copied out by the library)
             repr_out = {i - 1: torch.empty_like(x) for i in repr_layers if 0 < i < N}
             cos, sin = self._rope_tables(T)
-            attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out, list(range(N)) if need_head_weights else [])
+            attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out,
+                               list(range(N)) if need_head_weights else [], zero_pad_rows=True)
             for i, t in repr_out.items():
                 hidden[i + 1] = t
             # esm2.py:129 LM head, from the pre-LN stream (its first step is the same emb_layer_norm_after)
@@ -391,11 +393,10 @@ class ESM2(nn.Module):
             hidden[N] = x
         result = {"logits": logits, "representations": hidden}
         if need_head_weights:
-            attentions = attn_t["stacked"]  # B x L x H x T x T (esm2.py:134), written in place by the library
-            if bool(padding_mask.any()):  # esm2.py:135-139 (in place: the tensor is ours)
-                am = 1 - mask.type_as(attentions)
-                am = am.unsqueeze(1) * am.unsqueeze(2)
-                attentions.mul_(am[:, None, None, :, :])
+            # B x L x H x T x T (esm2.py:134), each layer written in place by the library; rows/columns of padded
+            # tokens are already zero (esm2.py:135-139: padded keys have probability 0, padded query rows are zeroed
+            # by the probability kernel), so no masking pass over the stack is needed
+            attentions = attn_t["stacked"]
             result["attentions"] = attentions
             if return_contacts:
                 result["contacts"] = self.contact_head(tokens, attentions)

@@ -91,12 +91,14 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
  *   repr_out[i]  NULL or fp32 [B,T,E]: copy of x after layer i (hidden_representations[i+1], esm2.py:117-118)
  *   attn_out[i]  NULL or fp32 [B,H,T,T]: attention probabilities of layer i (esm2.py:119-121); batch b starts at
  *                attn_out[i] + b * attn_batch_stride elements (0 = contiguous H*T*T), so the caller can point layer i
- *                into its slice of the stacked [B,L,H,T,T] result (esm2.py:134) and skip the torch.stack copy
+ *                into its slice of the stacked [B,L,H,T,T] result (esm2.py:134) and skip the torch.stack copy;
+ *                attn_flags bit 0: write the rows of padded QUERY tokens as zeros (esm2.py:135-139; padded key
+ *                columns are zero anyway), so the caller needs no masking pass over the stack
  * either array pointer itself may be NULL. */
 int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float* x, const uint8_t* pad_mask,
                           int32_t B, int32_t T, const float* rope_cos, const float* rope_sin,
-                          float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride,
+                          int32_t attn_flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Embedding prologue of ESM2.forward (esm2.py:84-95): gather from table [V,E], zero <mask> rows and rescale by
  * 0.88/(1 - n_mask/n_nonpad) when token_dropout, zero pad rows. tokens int64 [B,T] -> x fp32 [B,T,E]. */
