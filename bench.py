@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=GLOBAL_BATCH)
-    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--micro-batch", type=int, default=128)
     ap.add_argument("--ref-seqs", type=int, default=2, help="sequences per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-seqs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
