@@ -198,6 +198,7 @@ int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUt
       case EPI_LD_BATCH: e = launch_gemm2_epi<EPI_LD_BATCH>(ta, tb, *tout, p, num_sms(), st); break;
       case EPI_GELU_MATHONLY: e = launch_gemm2_epi<EPI_GELU_MATHONLY>(ta, tb, *tout, p, num_sms(), st); break;
       case EPI_F16_STOREONLY: e = launch_gemm2_epi<EPI_F16_STOREONLY>(ta, tb, *tout, p, num_sms(), st); break;
+      case EPI_FMA_MATHONLY: e = launch_gemm2_epi<EPI_FMA_MATHONLY>(ta, tb, *tout, p, num_sms(), st); break;
       default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
     }
     if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");
@@ -581,7 +582,7 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
   CUtensorMap ta, tb, tout;
   const bool v2 = gemm_version() == 2;
   const bool out_f16 = (epilogue == EPI_QKV_ROPE || epilogue == EPI_BIAS_GELU || epilogue == EPI_F16_STOREONLY ||
-                        epilogue == EPI_GELU_MATHONLY);
+                        epilogue == EPI_GELU_MATHONLY || epilogue == EPI_FMA_MATHONLY);
   rc = make_tmap_f16(&ta, a, M, K, K, gemm_cfg::BLOCK_M);
   if (!rc) rc = make_tmap_f16(&tb, w, N, K, K, v2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N);
   if (!rc && v2) rc = make_tmap_2d(&tout, out, out_f16 ? 2 : 4, M, N, N, 128);

@@ -23,7 +23,8 @@ enum : int { EPI_QKV_ROPE = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU = 2, EPI_BIA
               EPI_NONE = 5 /* profiling only: accumulators are discarded */,
               EPI_LDONLY = 6 /* profiling only: accumulators are read from TMEM and discarded */,
               EPI_LD_X16 = 7, EPI_LD_4WARPS = 8, EPI_LD_BATCH = 9 /* profiling only: TMEM read pattern variants */,
-              EPI_GELU_MATHONLY = 10, EPI_F16_STOREONLY = 11 /* profiling only: halves of the fc1 epilogue */ };
+              EPI_GELU_MATHONLY = 10, EPI_F16_STOREONLY = 11 /* profiling only: halves of the fc1 epilogue */,
+              EPI_FMA_MATHONLY = 12 /* profiling only: 15 dependent FMAs per element instead of GELU, no MUFU */ };
 
 struct GemmParams {
   int M, N, K;

@@ -168,7 +168,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + chalf * 128;
       const int col0 = n_blk * BLOCK_N + chalf * 128;
 
-      if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_GELU_MATHONLY || EPI == EPI_F16_STOREONLY) {
+      if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_GELU_MATHONLY || EPI == EPI_F16_STOREONLY ||
+                    EPI == EPI_FMA_MATHONLY) {
         // All four 32-column TMEM loads of this warp's 128 columns are issued back to back and retired by ONE
         // tcgen05.wait::ld: measured on B200 (profiles/r01_epilogue_experiments.txt) every extra ld->wait round trip
         // in the epilogue slows the concurrently running MMA mainloop (4 waits per tile: -15 %, 1 wait: -0 %).
@@ -187,7 +188,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int col = col0 + g * 64;
           if (col >= p.N) break;  // uniform over the 4 warps of this column half
           uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
-          if constexpr (EPI != EPI_GELU_MATHONLY) {
+          if constexpr (EPI != EPI_GELU_MATHONLY && EPI != EPI_FMA_MATHONLY) {
             if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two iterations ago has read it
             named_bar_sync(bar_id, 128);
           }
@@ -200,7 +201,15 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int v = 0; v < 4; ++v) {  // 8 columns -> one 16-byte chunk of the 128-byte staging row
               const float4 b0 = __ldg(b4 + 2 * v), b1 = __ldg(b4 + 2 * v + 1);
-              auto act = [](float x) { return EPI == EPI_F16_STOREONLY ? x : gelu_erf(x); };
+              auto act = [](float x) {
+                if constexpr (EPI == EPI_F16_STOREONLY) return x;
+                else if constexpr (EPI == EPI_FMA_MATHONLY) {
+                  float y = x;
+#pragma unroll
+                  for (int q = 0; q < 15; ++q) y = fmaf(y, x, 0.125f);
+                  return y;
+                } else return gelu_erf(x);
+              };
               const uint32_t o0 = pack_half2(act(__uint_as_float(a[8 * v + 0]) + b0.x),
                                              act(__uint_as_float(a[8 * v + 1]) + b0.y));
               const uint32_t o1 = pack_half2(act(__uint_as_float(a[8 * v + 2]) + b0.z),
@@ -209,7 +218,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                              act(__uint_as_float(a[8 * v + 5]) + b1.y));
               const uint32_t o3 = pack_half2(act(__uint_as_float(a[8 * v + 6]) + b1.z),
                                              act(__uint_as_float(a[8 * v + 7]) + b1.w));
-              if constexpr (EPI == EPI_GELU_MATHONLY) {
+              if constexpr (EPI == EPI_GELU_MATHONLY || EPI == EPI_FMA_MATHONLY) {
                 sink ^= o0 ^ o1 ^ o2 ^ o3;
               } else {
                 const uint32_t chunk = (uint32_t)(hf * 4 + v);
@@ -219,7 +228,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          if constexpr (EPI == EPI_GELU_MATHONLY) {
+          if constexpr (EPI == EPI_GELU_MATHONLY || EPI == EPI_FMA_MATHONLY) {
             if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
           } else {
             fence_proxy_async_smem();
