@@ -12,7 +12,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesmb200.so")
+LIB_PATH = os.environ.get("ESMB200_LIB_PATH") or os.path.join(_HERE, "libesmb200.so")  # override: developer builds
 
 # every symbol include/esmb200.h declares (tests/test_abi.py checks the .so exports exactly these)
 EXPORTS = (

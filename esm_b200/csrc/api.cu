@@ -620,6 +620,13 @@ int esmb200_mean_pool(const float* x, const int32_t* lengths, float* out, int32_
   return ESMB200_OK;
 }
 
+#ifdef ESMB200_TRACE
+int esmb200_debug_read_attn_trace(long long* out, int32_t n) {
+  CK(cudaMemcpyFromSymbol(out, esmb200::g_attn_trace, sizeof(long long) * (size_t)n));
+  return ESMB200_OK;
+}
+#endif
+
 long long esmb200_launch_count(void) { return g_prof.launches; }
 
 int esmb200_profile_enable(int32_t max_launches) {

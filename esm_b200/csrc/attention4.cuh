@@ -24,6 +24,14 @@
 
 namespace esmb200 {
 
+#ifdef ESMB200_TRACE
+// developer instrumentation (scripts/attn_trace.py): timestamps of CTA 0's softmax warp 2 / MMA thread
+__device__ long long g_attn_trace[8192];
+#define ATRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 400) g_attn_trace[(slot) * 400 + (idx)] = clock64(); } while (0)
+#else
+#define ATRACE(slot, idx) do { } while (0)
+#endif
+
 namespace attn4_cfg {
 constexpr int BLOCK_Q = 128;
 constexpr int BLOCK_KV = 64;
@@ -111,12 +119,12 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
         const int row_base = b * p.T;
         const uint32_t qb = tq & 1;
-        mbar_wait(&q_empty[qb], ((tq >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(&q_empty[qb], ((tq >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
         tma_load_2d(smem_q + qb * Q_BYTES, &tmap_q, &q_full[qb], h * HEAD_DIM, row_base + qt * BLOCK_Q);
         for (int i = 0; i < nblk; ++i, ++g) {
           const uint32_t s = g % KV_STAGES;
-          mbar_wait(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
+          mbar_wait_relaxed(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
           tma_load_2d(smem_k + s * KV_BYTES, &tmap_kv, &kv_full[s], p.E + h * HEAD_DIM, row_base + i * BLOCK_KV);
           tma_load_2d(smem_v + s * KV_BYTES, &tmap_kv, &kv_full[s], 2 * p.E + h * HEAD_DIM, row_base + i * BLOCK_KV);
@@ -167,7 +175,9 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int j = 0; j < nblk; ++j, ++gp) {
           while (gq < gp + 2 && qw < total) issue_next_qk();
           const uint32_t bf = gp & 1;
+          ATRACE(0, gp);
           mbar_wait(&p_full[bf], (gp >> 1) & 1);
+          ATRACE(1, gp);
           if (j == 0 && tp > 0) mbar_wait(o_free, (tp - 1) & 1);  // previous tile's O has been read out
           tc_fence_after();
           const uint32_t s = gp % KV_STAGES;
@@ -177,6 +187,7 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
             umma_ts(tmem_o, tmem_p + bf * 32 + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
           tc_commit(&pv_done[bf]);
           tc_commit(&kv_empty[s]);
+          ATRACE(2, gp);
         }
         ++tp;
       }
@@ -202,9 +213,15 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const uint32_t kw[2] = {kw2.x, kw2.y};
         const uint32_t ts = tmem_s + lane_addr + bf * 64;
         const uint32_t tp = tmem_p + lane_addr + bf * 32;
+        if (warp == 2 && lane == 0) ATRACE(4, g);
         mbar_wait(&s_full[bf], ph);
-        if (g >= 2) mbar_wait(&pv_done[bf], ph ^ 1);  // P.V(g-2) has finished reading P buffer bf
+        if (warp == 2 && lane == 0) ATRACE(5, g);
+        // P buffer bf was last read by P.V(g-2). No wait is needed for it: the MMA thread issued P.V(g-2) BEFORE
+        // Q.K^T(g), and s_full[g] is a tcgen05.commit placed after Q.K^T(g) — it fires only when every earlier MMA of
+        // that thread, P.V(g-2) included, has completed. (A separate pv_done wait here cost ~130 cycles per block:
+        // an mbarrier try_wait takes ~100 cycles even when the phase is long complete.)
         tc_fence_after();
+        if (warp == 2 && lane == 0) ATRACE(6, g);
         if (j == 0) {  // exact row max of the first block seeds the reference
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   #pragma unroll
@@ -232,6 +249,7 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_ld_32x32b_x32(ts + 32, sv[1]);
           tmem_wait_ld_dep(sv[0]);  // ONE tcgen05.wait::ld retires both loads (each extra wait slows the MMA pipe)
           reg_fence(sv[1]);
+          if (warp == 2 && lane == 0) ATRACE(7, g);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint32_t w = kw[c];

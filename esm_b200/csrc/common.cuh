@@ -103,6 +103,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+
+// Wait used by producer threads that run far ahead of their consumers (TMA rings): back off between polls so the
+// polling thread does not take issue slots from the compute warps sharing its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#if ESMB200_WATCHDOG
+  uint32_t polls = 0;
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+#if ESMB200_WATCHDOG
+    if (++polls == (1u << 24)) {
+      printf("esmb200: mbarrier watchdog (relaxed) block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+#endif
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D tile load global -> shared, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int a_row = m_blk * PAIR_M + rank * BLOCK_M;
         const int b_row = n_blk * BLOCK_N + rank * HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, a_row);
           tma_load_2d_pair(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
