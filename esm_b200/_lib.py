@@ -27,6 +27,7 @@ EXPORTS = (
     "esmb200_layernorm",
     "esmb200_mean_pool",
     "esmb200_gemm_f16",
+    "esmb200_gemm_qkv_f16",
     "esmb200_attention_scratch_bytes",
     "esmb200_attention",
     "esmb200_layernorm_f16",
@@ -103,6 +104,9 @@ def _declare(lib):
     lib.esmb200_gemm_f16.restype = c_int32
     lib.esmb200_gemm_f16.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.esmb200_gemm_qkv_f16.restype = c_int32
+    lib.esmb200_gemm_qkv_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p,
+                                         c_void_p, c_int32, c_void_p]
     lib.esmb200_attention_scratch_bytes.restype = c_size_t
     lib.esmb200_attention_scratch_bytes.argtypes = [c_int32, c_int32]
     lib.esmb200_attention.restype = c_int32

@@ -594,6 +594,27 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
   return launch_gemm(epilogue, ta, tb, v2 ? &tout : nullptr, g, static_cast<cudaStream_t>(stream));
 }
 
+int esmb200_gemm_qkv_f16(const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t E, float q_scale,
+                         const float* rope_cos, const float* rope_sin, int32_t T, void* stream) {
+  if (!a || !w || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
+  if (M <= 0 || E <= 0 || E % 64 != 0) return fail(ESMB200_EINVAL, "qkv gemm needs E % 64 == 0");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr) || (rope_cos && T <= 0))
+    return fail(ESMB200_EINVAL, "rope tables must be given together with T, or not at all");
+  int rc = check_device();
+  if (rc) return rc;
+  CUtensorMap ta, tb, tout;
+  const bool v2 = gemm_version() == 2;
+  rc = make_tmap_f16(&ta, a, M, E, E, gemm_cfg::BLOCK_M);
+  if (!rc) rc = make_tmap_f16(&tb, w, 3 * (uint64_t)E, E, E, v2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N);
+  if (!rc && v2) rc = make_tmap_2d(&tout, out, 2, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
+  if (rc) return rc;
+  GemmParams g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = 3 * E; g.K = E; g.bias = bias; g.out = out; g.ldo = 3 * E;
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T > 0 ? T : 1; g.E = E; g.q_scale = q_scale;
+  return launch_gemm(EPI_QKV_ROPE, ta, tb, v2 ? &tout : nullptr, g, static_cast<cudaStream_t>(stream));
+}
+
 int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,
                       int32_t H, void* scratch, void* stream) {
   if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");

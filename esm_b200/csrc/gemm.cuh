@@ -205,8 +205,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
                            __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
             float y1[4], y2[4];
-            if (sect < 2) {
-              const float sc = (sect == 0) ? p.q_scale : 1.0f;
+            const float sc = (sect == 0) ? p.q_scale : 1.0f;
+            if (sect < 2 && p.rope_cos != nullptr) {
               const float4 c = __ldg(cs4 + j4), s = __ldg(sn4 + j4);
               const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
@@ -218,7 +218,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               }
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { y1[e] = x1[e]; y2[e] = x2[e]; }
+              for (int e = 0; e < 4; ++e) { y1[e] = x1[e] * sc; y2[e] = x2[e] * sc; }
             }
             out_lo[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
             out_lo[2 * j4 + 1] = pack_half2(y1[2], y1[3]);

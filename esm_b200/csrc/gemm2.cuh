@@ -264,7 +264,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
                                  __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
             float y1[4], y2[4];
-            if (sect < 2) {
+            if (sect < 2 && p.rope_cos != nullptr) {
               const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
               const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
@@ -273,9 +273,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 y1[e] = a * cc[e] - b * ss[e];  // rotary_embedding.py:16-20 with rotate_half = cat(-x2, x1)
                 y2[e] = b * cc[e] + a * ss[e];
               }
-            } else {
+            } else {  // v, or q/k without rotary embedding (MSA axial attention): bias (+ q scale) only
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { y1[e] = x1[e]; y2[e] = x2[e]; }
+              for (int e = 0; e < 4; ++e) { y1[e] = x1[e] * sc; y2[e] = x2[e] * sc; }
             }
             outv[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
             outv[2 * j4 + 1] = pack_half2(y1[2], y1[3]);

@@ -1,0 +1,195 @@
+"""MSA-Transformer axial block on the sm_100a kernels — host-side mirror of
+/root/reference/esm/modules.py:145-221 (AxialTransformerLayer, NormalizedResidualBlock :360-392,
+FeedForwardNetwork :395-418) and /root/reference/esm/axial_attention.py (RowSelfAttention :11-130,
+ColumnSelfAttention :133-239), with the reference's parameter names so its state dicts load.
+
+First CUDA path for BASELINE.json configs[4].  Every matrix product runs in libesmb200.so:
+  * LayerNorm -> fp16, q/k/v projection (+ bias, q scale; no rotary embedding), out-projection + residual,
+    fc1 + erf-GELU, fc2 + residual: the same tcgen05 GEMM / LayerNorm kernels as the ESM-2 path;
+  * column attention: the tokens are regrouped column-major so that each alignment column is one "sequence" of R rows
+    for the tcgen05 flash-attention kernel;
+  * tied row attention (logits summed over the R rows, axial_attention.py:87): per head ONE GEMM with K = R*64
+    (Q' [C, R*64] x K'^T), a softmax over the C columns, and ONE GEMM P [C, C] x V' [C, R*64].
+PyTorch does the regrouping copies (permute().contiguous()) and the [H, C, C] softmax (12 MB at configs[4]); those are
+the parts a dedicated tied-attention kernel will absorb later.
+
+Limits of this first path: no padding inside the MSA (`self_attn_padding_mask` must be all False — configs[4] is a
+synthetic, unpadded MSA; the reference's -10000 / q-zeroing mask semantics are restated in oracle/msa_oracle.py),
+head_dim 64, inference only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .model import _ptr, _stream
+
+
+class _AttnParams(nn.Module):
+    """q/k/v/out projections under the reference's names (axial_attention.py:30-34, 151-155)."""
+
+    def __init__(self, embed_dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = embed_dim // num_heads
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+
+
+class _FFNParams(nn.Module):
+    def __init__(self, embed_dim: int, ffn_dim: int):
+        super().__init__()
+        self.fc1 = nn.Linear(embed_dim, ffn_dim)
+        self.fc2 = nn.Linear(ffn_dim, embed_dim)
+
+
+class _ResidualBlock(nn.Module):
+    """`layer` + `layer_norm` containers of NormalizedResidualBlock (modules.py:360-373)."""
+
+    def __init__(self, layer: nn.Module, embed_dim: int):
+        super().__init__()
+        self.layer = layer
+        self.layer_norm = nn.LayerNorm(embed_dim)
+
+
+def _gemm(epi: int, a16: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, out: torch.Tensor) -> None:
+    M, K = a16.shape
+    N = w16.shape[0]
+    _lib.check(_lib.load().esmb200_gemm_f16(epi, _ptr(a16), _ptr(w16), _ptr(bias), _ptr(out), M, N, K, None, None, 0, 0,
+                                            _stream()))
+
+
+def _ln16(x: torch.Tensor, ln: nn.LayerNorm, out16: torch.Tensor) -> None:
+    M, E = x.shape
+    _lib.check(_lib.load().esmb200_layernorm_f16(_ptr(x), _ptr(ln.weight), _ptr(ln.bias), _ptr(out16), M, E, ln.eps,
+                                                 _stream()))
+
+
+class AxialTransformerLayer(nn.Module):
+    """Drop-in for esm.modules.AxialTransformerLayer (modules.py:145-221) at inference."""
+
+    def __init__(self, embedding_dim: int = 768, ffn_embedding_dim: int = 3072, num_attention_heads: int = 8,
+                 dropout: float = 0.1, attention_dropout: float = 0.1, activation_dropout: float = 0.1,
+                 max_tokens_per_msa: int = 2 ** 14) -> None:
+        super().__init__()
+        if embedding_dim != 64 * num_attention_heads:
+            raise ValueError("esm_b200 supports head_dim == 64 only")
+        self.embedding_dim = embedding_dim
+        self.ffn_embedding_dim = ffn_embedding_dim
+        self.num_heads = num_attention_heads
+        self.row_self_attention = _ResidualBlock(_AttnParams(embedding_dim, num_attention_heads), embedding_dim)
+        self.column_self_attention = _ResidualBlock(_AttnParams(embedding_dim, num_attention_heads), embedding_dim)
+        self.feed_forward_layer = _ResidualBlock(_FFNParams(embedding_dim, ffn_embedding_dim), embedding_dim)
+        self._packed = None
+        self._packed_key = None
+
+    # ---- fp16 operand copies (re-made when a parameter changes) ------------------------------------------------
+    def _pack(self):
+        ps = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or key != self._packed_key:
+            def qkv(a):
+                w = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).detach().half().contiguous()
+                b = torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0).detach().float().contiguous()
+                return w, b
+            row, col, ffn = self.row_self_attention.layer, self.column_self_attention.layer, self.feed_forward_layer.layer
+            self._packed = {
+                "row_qkv": qkv(row), "col_qkv": qkv(col),
+                "row_out": row.out_proj.weight.detach().half().contiguous(),
+                "col_out": col.out_proj.weight.detach().half().contiguous(),
+                "fc1": ffn.fc1.weight.detach().half().contiguous(), "fc2": ffn.fc2.weight.detach().half().contiguous(),
+            }
+            self._packed_key = key
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, self_attn_mask: Optional[torch.Tensor] = None,
+                self_attn_padding_mask: Optional[torch.Tensor] = None, need_head_weights: bool = False):
+        """x: (R, C, B, E) like the reference (modules.py:195-221). Returns x, or (x, column_attn, row_attn)."""
+        if self_attn_mask is not None:
+            raise NotImplementedError
+        if not x.is_cuda:
+            raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self_attn_padding_mask is not None and bool(self_attn_padding_mask.any()):
+            raise NotImplementedError("the first MSA path handles unpadded MSAs only (see module docstring)")
+        R, C, B, E = x.shape
+        xb = x.permute(2, 0, 1, 3).contiguous().float()  # [B,R,C,E], updated in place by the residual epilogues
+        row_probs, col_probs = self._forward_batch_major(xb, need_head_weights)
+        out = xb.permute(1, 2, 0, 3).to(x.dtype)
+        if need_head_weights:
+            return out, col_probs, row_probs
+        return out
+
+    def _forward_batch_major(self, xb: torch.Tensor, need_probs: bool):
+        lib = _lib.load()
+        B, R, C, E = xb.shape
+        H, d, Fd = self.num_heads, 64, self.ffn_embedding_dim
+        M = B * R * C
+        dev = xb.device
+        pk = self._pack()
+        x2 = xb.view(M, E)
+        xn = torch.empty((M, E), dtype=torch.float16, device=dev)
+        qkv = torch.empty((M, 3 * E), dtype=torch.float16, device=dev)
+        ctx = torch.empty((M, E), dtype=torch.float16, device=dev)
+        with torch.cuda.device(dev):
+            # ================= tied row attention (axial_attention.py:71-111) =================
+            blk = self.row_self_attention
+            _ln16(x2, blk.layer_norm, xn)
+            w, b = pk["row_qkv"]
+            _lib.check(lib.esmb200_gemm_qkv_f16(_ptr(xn), _ptr(w), _ptr(b), _ptr(qkv), M, E,
+                                                (d ** -0.5) / math.sqrt(R), None, None, 0, _stream()))
+            Cp = (C + 63) // 64 * 64  # GEMM N / K granularity
+            q5 = qkv.view(B, R, C, 3, H, d)
+            zeros_c = torch.zeros(max(Cp, R * d), dtype=torch.float32, device=dev)
+            row_probs = torch.empty((H, B, C, C), dtype=torch.float32, device=dev) if need_probs else None
+            for bi in range(B):
+                qh = q5[bi, :, :, 0].permute(2, 1, 0, 3).reshape(H, C, R * d).contiguous()        # Q' [H, C, R*64]
+                kh = torch.zeros((H, Cp, R * d), dtype=torch.float16, device=dev)                  # K' padded rows
+                kh[:, :C] = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d)
+                vt = torch.zeros((H, R * d, Cp), dtype=torch.float16, device=dev)                  # V'^T [H, R*64, C]
+                vt[:, :, :C] = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C)
+                logits = torch.empty((H, C, Cp), dtype=torch.float32, device=dev)
+                for h in range(H):  # S_h = Q'_h K'_h^T : one GEMM with K = R*64 (the sum over rows of :87)
+                    _gemm(_lib.EPI_BIAS_F32, qh[h], kh[h], zeros_c, logits[h])
+                probs = torch.softmax(logits[:, :, :C], dim=-1)                                    # :105
+                if need_probs:
+                    row_probs[:, bi] = probs
+                p16 = torch.zeros((H, C, Cp), dtype=torch.float16, device=dev)
+                p16[:, :, :C] = probs
+                ctxh = torch.empty((H, C, R * d), dtype=torch.float32, device=dev)
+                for h in range(H):  # context'_h = P_h V'_h  (:108-109)
+                    _gemm(_lib.EPI_BIAS_F32, p16[h], vt[h], zeros_c, ctxh[h])
+                ctx.view(B, R, C, H, d)[bi] = ctxh.view(H, C, R, d).permute(2, 1, 0, 3)
+            _gemm(_lib.EPI_BIAS_RESIDUAL, ctx, pk["row_out"], blk.layer.out_proj.bias, x2)            # :110 + residual
+
+            # ================= column attention (axial_attention.py:182-222) =================
+            blk = self.column_self_attention
+            _ln16(x2, blk.layer_norm, xn)
+            w, b = pk["col_qkv"]
+            _lib.check(lib.esmb200_gemm_qkv_f16(_ptr(xn), _ptr(w), _ptr(b), _ptr(qkv), M, E, d ** -0.5, None, None, 0,
+                                                _stream()))
+            qkv_t = qkv.view(B, R, C, 3 * E).permute(0, 2, 1, 3).contiguous()                      # [B*C, R, 3E]
+            ctx_t = torch.empty((B * C * R, E), dtype=torch.float16, device=dev)
+            col_probs = torch.empty((B * C, H, R, R), dtype=torch.float32, device=dev) if need_probs else None
+            scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B * C, R), dtype=torch.uint8, device=dev)
+            _lib.check(lib.esmb200_attention(_ptr(qkv_t), None, _ptr(ctx_t), _ptr(col_probs), B * C, R, H, _ptr(scratch),
+                                             _stream()))
+            ctx.view(B, R, C, E).copy_(ctx_t.view(B, C, R, E).permute(0, 2, 1, 3))
+            _gemm(_lib.EPI_BIAS_RESIDUAL, ctx, pk["col_out"], blk.layer.out_proj.bias, x2)
+
+            # ================= feed-forward (modules.py:413-418) =================
+            blk = self.feed_forward_layer
+            _ln16(x2, blk.layer_norm, xn)
+            hbuf = torch.empty((M, Fd), dtype=torch.float16, device=dev)
+            _gemm(_lib.EPI_BIAS_GELU, xn, pk["fc1"], blk.layer.fc1.bias, hbuf)
+            _gemm(_lib.EPI_BIAS_RESIDUAL, hbuf, pk["fc2"], blk.layer.fc2.bias, x2)
+        if need_probs:
+            # reference shapes: column_attn [H, C, B, R, R] (axial_attention.py:206), row_attn [H, B, C, C] (:87)
+            col_probs = col_probs.view(B, C, H, R, R).permute(2, 1, 0, 3, 4).contiguous()
+        return row_probs, col_probs

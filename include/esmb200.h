@@ -123,6 +123,13 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a_f16, const void* w_f16, con
                      int32_t N, int32_t K, const float* rope_cos, const float* rope_sin, int32_t T, int32_t E,
                      void* stream);
 
+/* qkv[M,3E] fp16 = A[M,E] fp16 x [Wq;Wk;Wv]^T + bias, q columns scaled by q_scale, q/k rotated when rope tables are
+ * given (ESM-2: multihead_attention.py:258-261,354-355) or left unrotated when rope_cos == rope_sin == NULL (MSA axial
+ * attention: axial_attention.py:79-81 with q_scale = d^-1/2 / sqrt(rows), :199-202 with q_scale = d^-1/2). */
+int esmb200_gemm_qkv_f16(const void* a_f16, const void* w_qkv_f16, const float* bias_qkv, void* out_f16, int32_t M,
+                         int32_t E, float q_scale, const float* rope_cos, const float* rope_sin, int32_t T,
+                         void* stream);
+
 /* ctx[B*T,E] fp16 = softmax(q k^T + key padding mask) v per head, from qkv fp16 [B*T,3E] (q pre-scaled, q/k rotated).
  * scratch: at least esmb200_attention_scratch_bytes(B,T). attn_probs as in esmb200_layer_forward. */
 size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T);

@@ -1,0 +1,46 @@
+"""BASELINE.json configs[4]: esm_msa1b_t12_100M axial (row + column) attention forward on a synthetic 128 x 512 MSA,
+1xB200: 12 AxialTransformerLayers (E=768, H=12, F=3072), seeded random weights. Prints ms per MSA. Developer tool."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from esm_b200.msa import AxialTransformerLayer  # noqa: E402
+
+
+def main():
+    torch.manual_seed(0)
+    layers = [AxialTransformerLayer(768, 3072, 12).eval().cuda() for _ in range(12)]
+    R, C, B, E = 128, 512, 1, 768
+    x = torch.randn(R, C, B, E, device="cuda")
+
+    def fwd():
+        y = x
+        for l in layers:
+            y = l(y)
+        return y
+    for _ in range(2):
+        y = fwd()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    n = 5
+    for _ in range(n):
+        y = fwd()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    M = R * C
+    flops = 12 * (8 * 2 * M * E * E + 2 * 2 * M * E * 3072 + 2 * 2 * 12 * C * C * R * 64 + 4 * C * 12 * R * R * 64)
+    res = {"config": "12 x AxialTransformerLayer, MSA 128 x 512, E=768 H=12 (random init)", "ms_per_msa": round(ms, 3),
+           "msa_per_s": round(1e3 / ms, 2), "TFLOP/s": round(flops / ms / 1e9, 1), "finite": bool(torch.isfinite(y).all())}
+    print(json.dumps(res))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config5.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
