@@ -14,7 +14,7 @@ PyTorch does the regrouping copies (permute().contiguous()) and the [H, C, C] so
 the parts a dedicated tied-attention kernel will absorb later.
 
 Limits of this first path: no padding inside the MSA (`self_attn_padding_mask` must be all False — configs[4] is a
-synthetic, unpadded MSA; the reference's -10000 / q-zeroing mask semantics are restated in oracle/msa_oracle.py),
+synthetic, unpadded MSA; the reference's -10000 / q-zeroing mask semantics are not implemented on the GPU yet),
 head_dim 64, inference only.
 """
 from __future__ import annotations
