@@ -148,20 +148,28 @@ class AxialTransformerLayer(nn.Module):
             q5 = qkv.view(B, R, C, 3, H, d)
             zeros_c = torch.zeros(max(Cp, R * d), dtype=torch.float32, device=dev)
             row_probs = torch.empty((H, B, C, C), dtype=torch.float32, device=dev) if need_probs else None
+            padded = Cp != C
             for bi in range(B):
                 qh = q5[bi, :, :, 0].permute(2, 1, 0, 3).reshape(H, C, R * d).contiguous()        # Q' [H, C, R*64]
-                kh = torch.zeros((H, Cp, R * d), dtype=torch.float16, device=dev)                  # K' padded rows
-                kh[:, :C] = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d)
-                vt = torch.zeros((H, R * d, Cp), dtype=torch.float16, device=dev)                  # V'^T [H, R*64, C]
-                vt[:, :, :C] = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C)
+                if padded:  # zero rows / columns up to the GEMM granularity of 64
+                    kh = torch.zeros((H, Cp, R * d), dtype=torch.float16, device=dev)
+                    kh[:, :C] = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d)
+                    vt = torch.zeros((H, R * d, Cp), dtype=torch.float16, device=dev)
+                    vt[:, :, :C] = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C)
+                else:
+                    kh = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d).contiguous()    # K' [H, C, R*64]
+                    vt = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C).contiguous()    # V'^T [H, R*64, C]
                 logits = torch.empty((H, C, Cp), dtype=torch.float32, device=dev)
                 for h in range(H):  # S_h = Q'_h K'_h^T : one GEMM with K = R*64 (the sum over rows of :87)
                     _gemm(_lib.EPI_BIAS_F32, qh[h], kh[h], zeros_c, logits[h])
                 probs = torch.softmax(logits[:, :, :C], dim=-1)                                    # :105
                 if need_probs:
                     row_probs[:, bi] = probs
-                p16 = torch.zeros((H, C, Cp), dtype=torch.float16, device=dev)
-                p16[:, :, :C] = probs
+                if padded:
+                    p16 = torch.zeros((H, C, Cp), dtype=torch.float16, device=dev)
+                    p16[:, :, :C] = probs
+                else:
+                    p16 = probs.half()
                 ctxh = torch.empty((H, C, R * d), dtype=torch.float32, device=dev)
                 for h in range(H):  # context'_h = P_h V'_h  (:108-109)
                     _gemm(_lib.EPI_BIAS_F32, p16[h], vt[h], zeros_c, ctxh[h])

@@ -35,10 +35,21 @@ def main():
     ms = a.elapsed_time(b) / n
     M = R * C
     flops = 12 * (8 * 2 * M * E * E + 2 * 2 * M * E * 3072 + 2 * 2 * 12 * C * C * R * 64 + 4 * C * 12 * R * R * 64)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     res = {"config": "12 x AxialTransformerLayer, MSA 128 x 512, E=768 H=12 (random init)", "ms_per_msa": round(ms, 3),
            "msa_per_s": round(1e3 / ms, 2), "TFLOP/s": round(flops / ms / 1e9, 1), "finite": bool(torch.isfinite(y).all())}
+    # where the time goes: torch profiler, top CUDA kernels of one forward
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            fwd()
+            torch.cuda.synchronize()
+        tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70)
+        open(os.path.join(ROOT, "gpurun_out", "config5_profile.txt"), "w").write(tab)
+        print(tab[-3500:])
+    except Exception as e:  # profiler availability varies
+        print("profiler unavailable:", e)
     print(json.dumps(res))
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config5.json"), "w"), indent=1)
 
 
