@@ -41,7 +41,8 @@ MODEL = "esm2_t33_650M_UR50D"
 L_LAYERS, E, H, F = 33, 1280, 20, 5120
 GLOBAL_BATCH, SEQ_LEN = 256, 1024
 TAGS = ["ln1_f16", "gemm_qkv_rope", "attention", "gemm_out_residual", "ln2_f16", "gemm_fc1_gelu", "gemm_fc2_residual",
-        "key_bits", "embed", "layernorm_f32", "attention_probs", "convert", "gemm_other", "mean_pool"]
+        "key_bits", "embed", "layernorm_f32", "attention_probs", "convert", "gemm_other", "mean_pool",
+        "tied_row_logits", "tied_row_softmax", "tied_row_update"]
 
 
 def flops_per_seq(T=SEQ_LEN):

@@ -30,6 +30,9 @@ EXPORTS = (
     "esmb200_gemm_qkv_f16",
     "esmb200_attention_scratch_bytes",
     "esmb200_attention",
+    "esmb200_tied_row_attention_scratch_bytes",
+    "esmb200_tied_row_attention",
+    "esmb200_column_attention",
     "esmb200_layernorm_f16",
     "esmb200_convert_f16",
     "esmb200_launch_count",
@@ -112,6 +115,14 @@ def _declare(lib):
     lib.esmb200_attention.restype = c_int32
     lib.esmb200_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                       c_void_p]
+    lib.esmb200_tied_row_attention_scratch_bytes.restype = c_size_t
+    lib.esmb200_tied_row_attention_scratch_bytes.argtypes = [c_int32, c_int32, c_int32]
+    lib.esmb200_tied_row_attention.restype = c_int32
+    lib.esmb200_tied_row_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                               c_int32, c_void_p, c_size_t, c_void_p]
+    lib.esmb200_column_attention.restype = c_int32
+    lib.esmb200_column_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                             c_void_p]
     lib.esmb200_launch_count.restype = ctypes.c_longlong
     lib.esmb200_launch_count.argtypes = []
     lib.esmb200_profile_enable.restype = c_int32

@@ -21,6 +21,7 @@
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention5.cuh"
+#include "tied_attention.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -52,7 +53,7 @@ int fail_cuda(cudaError_t e, const char* what) {
 
 // ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) --------------------
 enum ProfTag : int { T_LN1 = 0, T_QKV, T_ATTN, T_OUT, T_LN2, T_FC1, T_FC2, T_KEYBITS, T_EMBED, T_LN_F32, T_PROBS,
-                     T_CONVERT, T_GEMM_OTHER, T_MEANPOOL, T_COUNT };
+                     T_CONVERT, T_GEMM_OTHER, T_MEANPOOL, T_TIED_SCORES, T_TIED_SOFTMAX, T_TIED_PV, T_COUNT };
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;  // pairs (start, stop)
@@ -624,6 +625,90 @@ int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float
   rc = run_key_bits(pad_mask, s, B, T, st);
   if (rc) return rc;
   return run_attention(qkv, ctx, attn_probs, 0, 0, s, B, T, H, st);
+}
+
+
+// ---- MSA axial attention (esm/axial_attention.py) -----------------------------------------------------------------
+size_t esmb200_tied_row_attention_scratch_bytes(int32_t B, int32_t C, int32_t H) {
+  const size_t Cp = align_up((size_t)C, 64);
+  return align_up((size_t)H * B * C * C * 4, 1024) + align_up((size_t)H * B * C * Cp * 2, 1024) + 2048;
+}
+
+int esmb200_tied_row_attention(const void* qkv, const uint8_t* key_pad, void* ctx, float* attn_probs, int32_t B,
+                               int32_t R, int32_t C, int32_t H, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || R <= 0 || C <= 0 || H <= 0 || H > 64 || (long long)B * H > 65535)
+    return fail(ESMB200_EINVAL, "bad shape");
+  if (C > TIED_MAX_C) return fail(ESMB200_EINVAL, "tied row attention supports at most 1024 alignment columns");
+  if (scratch_bytes < esmb200_tied_row_attention_scratch_bytes(B, C, H))
+    return fail(ESMB200_EWORKSPACE, "tied row attention scratch too small");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int E = H * 64;
+  const size_t Cp = align_up((size_t)C, 64);
+  uint8_t* sp = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(scratch), 1024));
+  TiedParams tp;
+  tp.B = B; tp.R = R; tp.C = C; tp.H = H; tp.E = E; tp.Cp = (int)Cp;
+  tp.S = attn_probs ? attn_probs : reinterpret_cast<float*>(sp);
+  tp.P = reinterpret_cast<__half*>(sp + align_up((size_t)H * B * C * C * 4, 1024));
+  tp.ctx = static_cast<__half*>(ctx);
+  tp.key_pad = key_pad;
+  tp.write_probs = attn_probs ? 1 : 0;
+  const uint64_t rows = (uint64_t)B * R * C;
+  CUtensorMap tq, tk, tv, tpm;
+  if ((rc = make_tmap_f16(&tq, qkv, rows, (uint64_t)3 * E, (uint64_t)3 * E, tied_cfg::S_BM))) return rc;
+  if ((rc = make_tmap_f16(&tk, qkv, rows, (uint64_t)3 * E, (uint64_t)3 * E, tied_cfg::S_BN))) return rc;
+  if ((rc = make_tmap_f16(&tv, qkv, rows, (uint64_t)3 * E, (uint64_t)3 * E, 64))) return rc;
+  if ((rc = make_tmap_f16(&tpm, tp.P, (uint64_t)H * B * C, Cp, Cp, tied_cfg::V_BM))) return rc;
+  cudaError_t e;
+  {
+    ProfScope ps(T_TIED_SCORES, st);
+    e = launch_tied_scores(tq, tk, tp, st);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "tied scores launch");
+  {
+    ProfScope ps(T_TIED_SOFTMAX, st);
+    e = launch_tied_softmax(tp, st);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "tied softmax launch");
+  {
+    ProfScope ps(T_TIED_PV, st);
+    e = launch_tied_pv(tpm, tv, tp, st);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "tied update launch");
+  return ESMB200_OK;
+}
+
+int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, int32_t B, int32_t R, int32_t C,
+                             int32_t H, void* scratch, void* stream) {
+  if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || R <= 0 || C <= 0 || H <= 0 || H > 64) return fail(ESMB200_EINVAL, "bad shape");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int E = H * 64;
+  const int S = B * C;  // one "sequence" of R tokens per alignment column
+  AttnScratch s = carve_attn_scratch(scratch, S, R, H);
+  rc = run_key_bits(pad_mask, s, S, R, st);
+  if (rc) return rc;
+  CUtensorMap tq, tkv;
+  const uint64_t wide = (uint64_t)C * 3 * E;  // qkv viewed as [B*R, C*3E]: token r of column c at row r, x = c*3E
+  if ((rc = make_tmap_f16(&tq, qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_Q))) return rc;
+  if ((rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_KV))) return rc;
+  AttnParams ap;
+  ap.B = S; ap.T = R; ap.H = H; ap.E = E;
+  ap.keybits = s.keybits; ap.kvlen = s.kvlen; ap.words = s.words;
+  ap.ctx = static_cast<__half*>(ctx);
+  ap.row_max = nullptr; ap.row_sum = nullptr;
+  ap.cols = C;
+  cudaError_t e;
+  {
+    ProfScope ps(T_ATTN, st);
+    e = launch_attention_v4(tq, tkv, ap, num_sms(), st);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
+  return ESMB200_OK;
 }
 
 

@@ -117,17 +117,18 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int nblk = n_blocks(w);
         if (nblk == 0) continue;
         const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
-        const int row_base = b * p.T;
+        const int row_base = (b / p.cols) * p.T;
+        const int x0 = (b % p.cols) * 3 * p.E + h * HEAD_DIM;
         const uint32_t qb = tq & 1;
         mbar_wait_relaxed(&q_empty[qb], ((tq >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
-        tma_load_2d(smem_q + qb * Q_BYTES, &tmap_q, &q_full[qb], h * HEAD_DIM, row_base + qt * BLOCK_Q);
+        tma_load_2d(smem_q + qb * Q_BYTES, &tmap_q, &q_full[qb], x0, row_base + qt * BLOCK_Q);
         for (int i = 0; i < nblk; ++i, ++g) {
           const uint32_t s = g % KV_STAGES;
           mbar_wait_relaxed(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
-          tma_load_2d(smem_k + s * KV_BYTES, &tmap_kv, &kv_full[s], p.E + h * HEAD_DIM, row_base + i * BLOCK_KV);
-          tma_load_2d(smem_v + s * KV_BYTES, &tmap_kv, &kv_full[s], 2 * p.E + h * HEAD_DIM, row_base + i * BLOCK_KV);
+          tma_load_2d(smem_k + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E, row_base + i * BLOCK_KV);
+          tma_load_2d(smem_v + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E, row_base + i * BLOCK_KV);
         }
         ++tq;
       }
@@ -201,7 +202,7 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
       const int nblk = n_blocks(w);
-      const int row_base = b * p.T;
+      const int row_base = (b / p.cols) * p.T;
       const int t = qt * BLOCK_Q + row_local;
       float m_ref = 0.f, l_run = 0.f;
       const uint32_t* kb_ptr = p.keybits + (size_t)b * p.words;
@@ -336,7 +337,7 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
           p.row_max[si] = m_ref;
           p.row_sum[si] = l_run;
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.ctx + (size_t)(row_base + t) * p.E + h * HEAD_DIM);
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * p.E + h * HEAD_DIM);
 #pragma unroll
         for (int v = 0; v < 8; ++v) dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
       }

@@ -3,19 +3,21 @@
 FeedForwardNetwork :395-418) and /root/reference/esm/axial_attention.py (RowSelfAttention :11-130,
 ColumnSelfAttention :133-239), with the reference's parameter names so its state dicts load.
 
-First CUDA path for BASELINE.json configs[4].  Every matrix product runs in libesmb200.so:
+CUDA path for BASELINE.json configs[4].  All the arithmetic of the block runs in libesmb200.so:
   * LayerNorm -> fp16, q/k/v projection (+ bias, q scale; no rotary embedding), out-projection + residual,
     fc1 + erf-GELU, fc2 + residual: the same tcgen05 GEMM / LayerNorm kernels as the ESM-2 path;
-  * column attention: the tokens are regrouped column-major so that each alignment column is one "sequence" of R rows
-    for the tcgen05 flash-attention kernel;
-  * tied row attention (logits summed over the R rows, axial_attention.py:87): per head ONE GEMM with K = R*64
-    (Q' [C, R*64] x K'^T), a softmax over the C columns, and ONE GEMM P [C, C] x V' [C, R*64].
-PyTorch does the regrouping copies (permute().contiguous()) and the [H, C, C] softmax (12 MB at configs[4]); those are
-the parts a dedicated tied-attention kernel will absorb later.
+  * tied row attention (logits summed over the R rows, axial_attention.py:87): esmb200_tied_row_attention — a tcgen05
+    contraction over K = R*64 that walks the alignment rows with TMA boxes taken straight from the projection output,
+    a row softmax (with the reference's -10000 fill on padded key columns), and the P.V update with V tiles as the
+    MN-major operand (csrc/tied_attention.cuh);
+  * column attention: esmb200_column_attention — the flash-attention kernel with strided TMA boxes, one "sequence" of
+    R rows per alignment column, no regrouping copy (csrc/attention4.cuh, AttnParams::cols).
+PyTorch is used for the buffers, for zeroing q at padded positions (axial_attention.py:82-85, one masked_fill_) and, only
+when the column attention MAPS are requested, for regrouping qkv column-major.
 
-Limits of this first path: no padding inside the MSA (`self_attn_padding_mask` must be all False — configs[4] is a
-synthetic, unpadded MSA; the reference's -10000 / q-zeroing mask semantics are not implemented on the GPU yet),
-head_dim 64, inference only.
+Padding: the reference fills padded keys with -10000, this path gives them probability exactly 0 in the column
+attention — identical unless every key of a column is padded (there the reference averages v uniformly, this path
+returns 0); such positions are themselves padding.  head_dim 64, inference only.
 """
 from __future__ import annotations
 
@@ -111,22 +113,26 @@ class AxialTransformerLayer(nn.Module):
     @torch.no_grad()
     def forward(self, x: torch.Tensor, self_attn_mask: Optional[torch.Tensor] = None,
                 self_attn_padding_mask: Optional[torch.Tensor] = None, need_head_weights: bool = False):
-        """x: (R, C, B, E) like the reference (modules.py:195-221). Returns x, or (x, column_attn, row_attn)."""
+        """x: (R, C, B, E) like the reference (modules.py:195-221); self_attn_padding_mask: (B, R, C) bool.
+        Returns x, or (x, column_attn, row_attn)."""
         if self_attn_mask is not None:
             raise NotImplementedError
         if not x.is_cuda:
             raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if self_attn_padding_mask is not None and bool(self_attn_padding_mask.any()):
-            raise NotImplementedError("the first MSA path handles unpadded MSAs only (see module docstring)")
         R, C, B, E = x.shape
         xb = x.permute(2, 0, 1, 3).contiguous().float()  # [B,R,C,E], updated in place by the residual epilogues
-        row_probs, col_probs = self._forward_batch_major(xb, need_head_weights)
+        row_probs, col_probs = self.forward_batch_major(xb, self_attn_padding_mask, need_head_weights)
         out = xb.permute(1, 2, 0, 3).to(x.dtype)
         if need_head_weights:
             return out, col_probs, row_probs
         return out
 
-    def _forward_batch_major(self, xb: torch.Tensor, need_probs: bool):
+    @torch.no_grad()
+    def forward_batch_major(self, xb: torch.Tensor, padding_mask: Optional[torch.Tensor] = None,
+                            need_probs: bool = False):
+        """In-place layer on the batch-major residual stream xb [B,R,C,E] fp32 (what MSATransformer keeps between
+        layers).  padding_mask [B,R,C] bool or None.  Returns (row_attn [H,B,C,C], column_attn [H,C,B,R,R]) or
+        (None, None)."""
         lib = _lib.load()
         B, R, C, E = xb.shape
         H, d, Fd = self.num_heads, 64, self.ffn_embedding_dim
@@ -137,6 +143,11 @@ class AxialTransformerLayer(nn.Module):
         xn = torch.empty((M, E), dtype=torch.float16, device=dev)
         qkv = torch.empty((M, 3 * E), dtype=torch.float16, device=dev)
         ctx = torch.empty((M, E), dtype=torch.float16, device=dev)
+        key_pad = col_pad = None
+        if padding_mask is not None:
+            pm = padding_mask.to(device=dev, dtype=torch.bool)
+            key_pad = pm[:, 0].contiguous().to(torch.uint8)                    # [B,C]   axial_attention.py:94-97
+            col_pad = pm.permute(0, 2, 1).contiguous().to(torch.uint8)         # [B*C,R] axial_attention.py:212-215
         with torch.cuda.device(dev):
             # ================= tied row attention (axial_attention.py:71-111) =================
             blk = self.row_self_attention
@@ -144,36 +155,13 @@ class AxialTransformerLayer(nn.Module):
             w, b = pk["row_qkv"]
             _lib.check(lib.esmb200_gemm_qkv_f16(_ptr(xn), _ptr(w), _ptr(b), _ptr(qkv), M, E,
                                                 (d ** -0.5) / math.sqrt(R), None, None, 0, _stream()))
-            Cp = (C + 63) // 64 * 64  # GEMM N / K granularity
-            q5 = qkv.view(B, R, C, 3, H, d)
-            zeros_c = torch.zeros(max(Cp, R * d), dtype=torch.float32, device=dev)
+            if padding_mask is not None:  # q zeroed at padded positions (:82-85)
+                qkv.view(B, R, C, 3, E)[:, :, :, 0].masked_fill_(pm[..., None], 0)
             row_probs = torch.empty((H, B, C, C), dtype=torch.float32, device=dev) if need_probs else None
-            padded = Cp != C
-            for bi in range(B):
-                qh = q5[bi, :, :, 0].permute(2, 1, 0, 3).reshape(H, C, R * d).contiguous()        # Q' [H, C, R*64]
-                if padded:  # zero rows / columns up to the GEMM granularity of 64
-                    kh = torch.zeros((H, Cp, R * d), dtype=torch.float16, device=dev)
-                    kh[:, :C] = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d)
-                    vt = torch.zeros((H, R * d, Cp), dtype=torch.float16, device=dev)
-                    vt[:, :, :C] = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C)
-                else:
-                    kh = q5[bi, :, :, 1].permute(2, 1, 0, 3).reshape(H, C, R * d).contiguous()    # K' [H, C, R*64]
-                    vt = q5[bi, :, :, 2].permute(2, 0, 3, 1).reshape(H, R * d, C).contiguous()    # V'^T [H, R*64, C]
-                logits = torch.empty((H, C, Cp), dtype=torch.float32, device=dev)
-                for h in range(H):  # S_h = Q'_h K'_h^T : one GEMM with K = R*64 (the sum over rows of :87)
-                    _gemm(_lib.EPI_BIAS_F32, qh[h], kh[h], zeros_c, logits[h])
-                probs = torch.softmax(logits[:, :, :C], dim=-1)                                    # :105
-                if need_probs:
-                    row_probs[:, bi] = probs
-                if padded:
-                    p16 = torch.zeros((H, C, Cp), dtype=torch.float16, device=dev)
-                    p16[:, :, :C] = probs
-                else:
-                    p16 = probs.half()
-                ctxh = torch.empty((H, C, R * d), dtype=torch.float32, device=dev)
-                for h in range(H):  # context'_h = P_h V'_h  (:108-109)
-                    _gemm(_lib.EPI_BIAS_F32, p16[h], vt[h], zeros_c, ctxh[h])
-                ctx.view(B, R, C, H, d)[bi] = ctxh.view(H, C, R, d).permute(2, 1, 0, 3)
+            nbytes = lib.esmb200_tied_row_attention_scratch_bytes(B, C, H)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.esmb200_tied_row_attention(_ptr(qkv), _ptr(key_pad), _ptr(ctx), _ptr(row_probs), B, R, C, H,
+                                                      _ptr(scratch), nbytes, _stream()))
             _gemm(_lib.EPI_BIAS_RESIDUAL, ctx, pk["row_out"], blk.layer.out_proj.bias, x2)            # :110 + residual
 
             # ================= column attention (axial_attention.py:182-222) =================
@@ -182,13 +170,18 @@ class AxialTransformerLayer(nn.Module):
             w, b = pk["col_qkv"]
             _lib.check(lib.esmb200_gemm_qkv_f16(_ptr(xn), _ptr(w), _ptr(b), _ptr(qkv), M, E, d ** -0.5, None, None, 0,
                                                 _stream()))
-            qkv_t = qkv.view(B, R, C, 3 * E).permute(0, 2, 1, 3).contiguous()                      # [B*C, R, 3E]
-            ctx_t = torch.empty((B * C * R, E), dtype=torch.float16, device=dev)
-            col_probs = torch.empty((B * C, H, R, R), dtype=torch.float32, device=dev) if need_probs else None
             scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B * C, R), dtype=torch.uint8, device=dev)
-            _lib.check(lib.esmb200_attention(_ptr(qkv_t), None, _ptr(ctx_t), _ptr(col_probs), B * C, R, H, _ptr(scratch),
-                                             _stream()))
-            ctx.view(B, R, C, E).copy_(ctx_t.view(B, C, R, E).permute(0, 2, 1, 3))
+            col_probs = None
+            if not need_probs:  # q/k/v tiles are fetched straight from the row-major qkv (strided TMA boxes)
+                _lib.check(lib.esmb200_column_attention(_ptr(qkv), _ptr(col_pad), _ptr(ctx), B, R, C, H, _ptr(scratch),
+                                                        _stream()))
+            else:               # probabilities requested: regroup column-major and use the probs-writing path
+                qkv_t = qkv.view(B, R, C, 3 * E).permute(0, 2, 1, 3).contiguous()                  # [B*C, R, 3E]
+                ctx_t = torch.empty((B * C * R, E), dtype=torch.float16, device=dev)
+                col_probs = torch.empty((B * C, H, R, R), dtype=torch.float32, device=dev)
+                _lib.check(lib.esmb200_attention(_ptr(qkv_t), _ptr(col_pad), _ptr(ctx_t), _ptr(col_probs), B * C, R, H,
+                                                 _ptr(scratch), _stream()))
+                ctx.view(B, R, C, E).copy_(ctx_t.view(B, C, R, E).permute(0, 2, 1, 3))
             _gemm(_lib.EPI_BIAS_RESIDUAL, ctx, pk["col_out"], blk.layer.out_proj.bias, x2)
 
             # ================= feed-forward (modules.py:413-418) =================

@@ -136,6 +136,22 @@ size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T);
 int esmb200_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, float* attn_probs, int32_t B,
                       int32_t T, int32_t H, void* scratch, void* stream);
 
+/* ---- MSA Transformer axial attention on qkv fp16 [B*R*C, 3E] (B alignments, R rows, C columns; q pre-scaled) ----
+ * esmb200_tied_row_attention: RowSelfAttention.compute_attention_weights / compute_attention_update,
+ *   esm/axial_attention.py:71-111 — logits summed over the R rows (:87), key_pad [B,C] (1 = padded key column, filled
+ *   with -10000, :94-97; NULL = none), softmax over the key columns (:105), ctx[B*R*C,E] fp16 = P v per row (:108).
+ *   The caller zeroes q at padded positions (:82-85). attn_probs: optional fp32 [H,B,C,C] (the reference's return
+ *   layout), NULL to skip. scratch: esmb200_tied_row_attention_scratch_bytes(B,C,H). C <= 1024.
+ * esmb200_column_attention: ColumnSelfAttention.compute_attention_update, esm/axial_attention.py:182-222 — per
+ *   alignment column, attention over the R rows; pad_mask [B*C, R] (1 = padded key; such keys get probability 0 where
+ *   the reference fills -10000, identical unless every key of a column is padded), ctx[B*R*C,E] fp16.
+ *   scratch: esmb200_attention_scratch_bytes(B*C, R). */
+size_t esmb200_tied_row_attention_scratch_bytes(int32_t B, int32_t C, int32_t H);
+int esmb200_tied_row_attention(const void* qkv_f16, const uint8_t* key_pad, void* ctx_f16, float* attn_probs, int32_t B,
+                               int32_t R, int32_t C, int32_t H, void* scratch, size_t scratch_bytes, void* stream);
+int esmb200_column_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, int32_t B, int32_t R,
+                             int32_t C, int32_t H, void* scratch, void* stream);
+
 /* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,
                           float eps, void* stream);
@@ -146,7 +162,8 @@ int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias
  *   (0 disables and frees the events); esmb200_profile_read returns up to max_records (tag, milliseconds) pairs,
  *   synchronising on the recorded events, and resets the record list.
  *   tags: 0 LN1->f16, 1 QKV+RoPE GEMM, 2 attention, 3 out-proj GEMM, 4 LN2->f16, 5 fc1+GELU GEMM, 6 fc2 GEMM,
- *         7 key bits, 8 embed, 9 LayerNorm fp32, 10 attention probs, 11 convert, 12 other GEMM, 13 mean pool */
+ *         7 key bits, 8 embed, 9 LayerNorm fp32, 10 attention probs, 11 convert, 12 other GEMM, 13 mean pool,
+ *         14 tied row logits, 15 tied row softmax, 16 tied row update */
 long long esmb200_launch_count(void);
 int esmb200_profile_enable(int32_t max_launches);
 int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records);

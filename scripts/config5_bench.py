@@ -15,12 +15,12 @@ def main():
     torch.manual_seed(0)
     layers = [AxialTransformerLayer(768, 3072, 12).eval().cuda() for _ in range(12)]
     R, C, B, E = 128, 512, 1, 768
-    x = torch.randn(R, C, B, E, device="cuda")
+    x = torch.randn(B, R, C, E, device="cuda")  # batch-major residual stream, as the model keeps it between layers
 
     def fwd():
-        y = x
+        y = x.clone()
         for l in layers:
-            y = l(y)
+            l.forward_batch_major(y)  # in place
         return y
     for _ in range(2):
         y = fwd()

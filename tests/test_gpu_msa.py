@@ -47,10 +47,39 @@ def test_axial_layer_against_oracle_msa1b_width():
     assert rel_fro(out.permute(2, 0, 1, 3).cpu(), ref) <= 3e-3
 
 
-def test_padded_msa_is_refused_not_silently_wrong():
-    layer, _ = build(128, 512, 2)
-    x = torch.randn(4, 10, 1, 128).cuda()
-    mask = torch.zeros(1, 4, 10, dtype=torch.bool).cuda()
-    mask[0, :, -1] = True
-    with pytest.raises(NotImplementedError):
-        layer(x, self_attn_padding_mask=mask)
+def test_padded_msas_against_reference_golden(golden_dir):
+    """Two MSAs padded the way MSABatchConverter pads (trailing columns; trailing rows of the second MSA): q zeroing,
+    -10000 key fill in the row attention, padded keys in the column attention. Padding positions themselves are not
+    compared (fully padded columns: the reference averages v uniformly, this path writes 0 — documented deviation)."""
+    fx = torch.load(os.path.join(golden_dir, "msa_small_E128_H2.pt"), weights_only=False)
+    cfg, mask = fx["config"], fx["mask"]
+    g = torch.Generator().manual_seed(cfg["x_seed"])
+    x = torch.randn(cfg["B"], cfg["R"], cfg["C"], cfg["E"], generator=g)
+    layer, _ = build(cfg["E"], cfg["F"], cfg["H"])
+    keep = ~mask
+    for need in (False, True):
+        res = layer(x.permute(1, 2, 0, 3).cuda(), self_attn_padding_mask=mask.cuda(), need_head_weights=need)
+        out = (res[0] if need else res).permute(2, 0, 1, 3).cpu()
+        assert torch.isfinite(out).all()
+        assert rel_fro(out[keep], fx["out"][keep]) <= 3e-3
+        if need:
+            assert float((res[2].cpu() - fx["row_attn"]).abs().max()) <= 1e-2
+            col = res[1][:, :4].cpu()                       # [H, 4 columns, B, R, R]; columns 0-3 are not padding
+            qkeep = keep[:, :, :4].permute(2, 0, 1)         # [4, B, R]: query rows that are not padding
+            assert float((col - fx["col_attn_sample"]).abs()[:, qkeep].max()) <= 1e-2
+
+
+@pytest.mark.parametrize("B,R,C", [(1, 10, 77), (2, 5, 130), (1, 3, 300)])
+def test_axial_layer_ragged_shapes_against_oracle(B, R, C):
+    """Row counts that are not a multiple of the 4-row update tile, column counts that are not multiples of 64 / 4."""
+    from oracle import msa_oracle
+    layer, sd = build(128, 512, 2)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, R, C, 128, generator=g)
+    ref, col_ref, row_ref = msa_oracle.axial_layer(x, sd, "layers.0.", 2, need_head_weights=True)
+    out = layer(x.permute(1, 2, 0, 3).cuda())
+    assert rel_fro(out.permute(2, 0, 1, 3).cpu(), ref) <= 3e-3
+    out2, col, row = layer(x.permute(1, 2, 0, 3).cuda(), need_head_weights=True)
+    assert rel_fro(out2.permute(2, 0, 1, 3).cpu(), ref) <= 3e-3
+    assert float((row.cpu() - row_ref).abs().max()) <= 1e-2
+    assert float((col.cpu() - col_ref).abs().max()) <= 1e-2
