@@ -33,6 +33,9 @@ EXPORTS = (
     "esmb200_tied_row_attention_scratch_bytes",
     "esmb200_tied_row_attention",
     "esmb200_column_attention",
+    "esmb200_axial_workspace_bytes",
+    "esmb200_axial_stack_forward",
+    "esmb200_msa_embed",
     "esmb200_layernorm_f16",
     "esmb200_convert_f16",
     "esmb200_launch_count",
@@ -123,6 +126,15 @@ def _declare(lib):
     lib.esmb200_column_attention.restype = c_int32
     lib.esmb200_column_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                              c_void_p]
+    lib.esmb200_axial_workspace_bytes.restype = c_size_t
+    lib.esmb200_axial_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
+    lib.esmb200_axial_stack_forward.restype = c_int32
+    lib.esmb200_axial_stack_forward.argtypes = [POINTER(c_void_p), POINTER(c_void_p), c_int32, c_void_p, c_void_p,
+                                                c_void_p, c_int32, c_int32, c_int32, POINTER(c_void_p), c_void_p,
+                                                c_size_t, c_void_p]
+    lib.esmb200_msa_embed.restype = c_int32
+    lib.esmb200_msa_embed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.esmb200_launch_count.restype = ctypes.c_longlong
     lib.esmb200_launch_count.argtypes = []
     lib.esmb200_profile_enable.restype = c_int32

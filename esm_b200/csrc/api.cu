@@ -350,11 +350,12 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   const int E = w->embed_dim, H = w->num_heads, F = w->ffn_dim;
   if (E <= 0 || H <= 0 || E != H * 64)
     return fail(ESMB200_EINVAL, "esmb200 supports head_dim == 64 only (embed_dim must equal 64 * num_heads)");
-  if (F <= 0 || F % 64 != 0) return fail(ESMB200_EINVAL, "ffn_dim must be a positive multiple of 64");
+  const bool has_ffn = w->fc1_weight != nullptr;  // NULL fc1_weight: attention-only layer (MSA row-attention sub-layer)
+  if (has_ffn && (F <= 0 || F % 64 != 0)) return fail(ESMB200_EINVAL, "ffn_dim must be a positive multiple of 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   esmb200_layer* L = new esmb200_layer();
   memset(static_cast<void*>(L), 0, sizeof(*L));
-  L->E = E; L->H = H; L->F = F; L->eps = w->ln_eps;
+  L->E = E; L->H = H; L->F = has_ffn ? F : 0; L->eps = w->ln_eps;
   L->ln1_w = w->ln1_weight; L->ln1_b = w->ln1_bias; L->ln2_w = w->ln2_weight; L->ln2_b = w->ln2_bias;
   L->out_b = w->out_bias; L->fc1_b = w->fc1_bias; L->fc2_b = w->fc2_bias;
   const size_t EE = (size_t)E * E, EF = (size_t)E * F;
@@ -366,16 +367,18 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   }
   ALLOC(L->w_qkv, 3 * EE * 2);
   ALLOC(L->w_out, EE * 2);
-  ALLOC(L->w_fc1, EF * 2);
-  ALLOC(L->w_fc2, EF * 2);
+  if (has_ffn) {
+    ALLOC(L->w_fc1, EF * 2);
+    ALLOC(L->w_fc2, EF * 2);
+  }
   ALLOC(L->b_qkv, (size_t)3 * E * 4);
 #undef ALLOC
   rc = esmb200_convert_f16(w->q_weight, L->w_qkv, EE, stream);
   if (!rc) rc = esmb200_convert_f16(w->k_weight, L->w_qkv + EE, EE, stream);
   if (!rc) rc = esmb200_convert_f16(w->v_weight, L->w_qkv + 2 * EE, EE, stream);
   if (!rc) rc = esmb200_convert_f16(w->out_weight, L->w_out, EE, stream);
-  if (!rc) rc = esmb200_convert_f16(w->fc1_weight, L->w_fc1, EF, stream);
-  if (!rc) rc = esmb200_convert_f16(w->fc2_weight, L->w_fc2, EF, stream);
+  if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc1_weight, L->w_fc1, EF, stream);
+  if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc2_weight, L->w_fc2, EF, stream);
   if (!rc) {
     e = cudaMemcpyAsync(L->b_qkv, w->q_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + E, w->k_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
@@ -385,8 +388,8 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   const uint32_t wbox = gemm_version() == 2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N;
   if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)E, E, E, wbox);
   if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, E, E, wbox);
-  if (!rc) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
-  if (!rc) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, wbox);
+  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
+  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, wbox);
   if (rc) {
     esmb200_layer_destroy(L);
     return rc;
@@ -509,6 +512,7 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int E = layers[0]->E, F = layers[0]->F;
+  if (F <= 0) return fail(ESMB200_EINVAL, "attention-only layers belong to esmb200_axial_stack_forward");
   for (int i = 1; i < n_layers; ++i)
     if (layers[i]->E != E || layers[i]->F != F) return fail(ESMB200_EINVAL, "layers of one stack must share E and F");
   Workspace ws;
@@ -634,8 +638,9 @@ size_t esmb200_tied_row_attention_scratch_bytes(int32_t B, int32_t C, int32_t H)
   return align_up((size_t)H * B * C * C * 4, 1024) + align_up((size_t)H * B * C * Cp * 2, 1024) + 2048;
 }
 
-int esmb200_tied_row_attention(const void* qkv, const uint8_t* key_pad, void* ctx, float* attn_probs, int32_t B,
-                               int32_t R, int32_t C, int32_t H, void* scratch, size_t scratch_bytes, void* stream) {
+static int tied_row_impl(const void* qkv, const uint8_t* key_pad, long long key_pad_stride, void* ctx,
+                         float* attn_probs, int32_t B, int32_t R, int32_t C, int32_t H, void* scratch,
+                         size_t scratch_bytes, void* stream) {
   if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");
   if (B <= 0 || R <= 0 || C <= 0 || H <= 0 || H > 64 || (long long)B * H > 65535)
     return fail(ESMB200_EINVAL, "bad shape");
@@ -654,6 +659,7 @@ int esmb200_tied_row_attention(const void* qkv, const uint8_t* key_pad, void* ct
   tp.P = reinterpret_cast<__half*>(sp + align_up((size_t)H * B * C * C * 4, 1024));
   tp.ctx = static_cast<__half*>(ctx);
   tp.key_pad = key_pad;
+  tp.key_pad_stride = key_pad_stride;
   tp.write_probs = attn_probs ? 1 : 0;
   const uint64_t rows = (uint64_t)B * R * C;
   CUtensorMap tq, tk, tv, tpm;
@@ -678,6 +684,11 @@ int esmb200_tied_row_attention(const void* qkv, const uint8_t* key_pad, void* ct
   }
   if (e != cudaSuccess) return fail_cuda(e, "tied update launch");
   return ESMB200_OK;
+}
+
+int esmb200_tied_row_attention(const void* qkv, const uint8_t* key_pad, void* ctx, float* attn_probs, int32_t B,
+                               int32_t R, int32_t C, int32_t H, void* scratch, size_t scratch_bytes, void* stream) {
+  return tied_row_impl(qkv, key_pad, C, ctx, attn_probs, B, R, C, H, scratch, scratch_bytes, stream);
 }
 
 int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, int32_t B, int32_t R, int32_t C,
@@ -708,6 +719,142 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
     e = launch_attention_v4(tq, tkv, ap, num_sms(), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
+  return ESMB200_OK;
+}
+
+
+size_t esmb200_axial_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t R, int32_t C) {
+  return esmb200_workspace_bytes(E, F, B * C, R) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
+}
+
+int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer* const* col_layers, int32_t n_layers,
+                                float* x, const uint8_t* pad_mask, const uint8_t* col_pad_mask, int32_t B, int32_t R,
+                                int32_t C, float* const* row_attn_out, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!row_layers || !col_layers || n_layers <= 0 || !x || !workspace) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || R <= 0 || C <= 0) return fail(ESMB200_EINVAL, "empty alignment");
+  if ((pad_mask == nullptr) != (col_pad_mask == nullptr))
+    return fail(ESMB200_EINVAL, "pad_mask [B,R,C] and col_pad_mask [B,C,R] must be given together");
+  if ((long long)B * R * C > 0x7fffffffLL / 8) return fail(ESMB200_EINVAL, "B*R*C too large for one call");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int E = col_layers[0]->E, F = col_layers[0]->F, H = col_layers[0]->H;
+  if (F <= 0) return fail(ESMB200_EINVAL, "col_layers carry the feed-forward weights");
+  for (int i = 0; i < n_layers; ++i)
+    if (row_layers[i]->E != E || col_layers[i]->E != E || col_layers[i]->F != F)
+      return fail(ESMB200_EINVAL, "layers of one stack must share E and F");
+  if (workspace_bytes < esmb200_axial_workspace_bytes(E, F, B, R, C))
+    return fail(ESMB200_EWORKSPACE, "workspace too small");
+  const int M = B * R * C;
+  Workspace ws;
+  const size_t base_bytes = esmb200_workspace_bytes(E, F, B * C, R);
+  rc = carve_workspace(&ws, workspace, base_bytes, E, F, B * C, R);
+  if (rc) return rc;
+  uint8_t* tied_scratch = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024)) + base_bytes;
+  const size_t tied_bytes = esmb200_tied_row_attention_scratch_bytes(B, C, H);
+  ActMaps am;
+  rc = make_act_maps(&am, ws, x, E, F, M);
+  if (rc) return rc;
+  rc = run_key_bits(col_pad_mask, ws.as, B * C, R, st);  // column attention: B*C sequences of R keys
+  if (rc) return rc;
+  CUtensorMap tcq, tckv;
+  const uint64_t wide = (uint64_t)C * 3 * E;
+  if ((rc = make_tmap_f16(&tcq, ws.qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_Q))) return rc;
+  if ((rc = make_tmap_f16(&tckv, ws.qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_KV))) return rc;
+  const float row_scale = 0.125f / sqrtf((float)R);  // axial_attention.py:36-38
+  cudaError_t e;
+  GemmParams g;
+  for (int i = 0; i < n_layers; ++i) {
+    // ---------------- tied row attention (modules.py:202-207; axial_attention.py:71-130) ----------------
+    esmb200_layer* L = row_layers[i];
+    {
+      ProfScope ps(T_LN1, st);
+      e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "row layernorm");
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
+    g.T = 1; g.E = E; g.q_scale = row_scale;
+    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
+    if (rc) return rc;
+    if (pad_mask) {
+      ProfScope ps(T_KEYBITS, st);
+      zero_q_at_pads_kernel<<<(M + 7) / 8, 256, 0, st>>>(ws.qkv, pad_mask, M, E);
+      CK(cudaGetLastError());
+    }
+    rc = tied_row_impl(ws.qkv, pad_mask, (long long)R * C, ws.ctx, row_attn_out ? row_attn_out[i] : nullptr, B, R, C, H,
+                       tied_scratch, tied_bytes, stream);
+    if (rc) return rc;
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
+    if (rc) return rc;
+    // ---------------- column attention (modules.py:208-212; axial_attention.py:182-239) ----------------
+    L = col_layers[i];
+    {
+      ProfScope ps(T_LN1, st);
+      e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "column layernorm");
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
+    g.T = 1; g.E = E; g.q_scale = 0.125f;
+    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
+    if (rc) return rc;
+    {
+      AttnParams ap;
+      ap.B = B * C; ap.T = R; ap.H = H; ap.E = E;
+      ap.keybits = ws.as.keybits; ap.kvlen = ws.as.kvlen; ap.words = ws.as.words;
+      ap.ctx = ws.ctx; ap.row_max = nullptr; ap.row_sum = nullptr; ap.cols = C;
+      ProfScope ps(T_ATTN, st);
+      e = launch_attention_v4(tcq, tckv, ap, num_sms(), st);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
+    if (rc) return rc;
+    // ---------------- feed-forward (modules.py:213-214, 413-418) ----------------
+    {
+      ProfScope ps(T_LN2, st);
+      e = launch_layernorm<true>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "ffn layernorm");
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
+    rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.v2 ? &am.h : nullptr, g, st, T_FC1);
+    if (rc) return rc;
+    memset(&g, 0, sizeof g);
+    g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.v2 ? &am.x_out : nullptr, g, st, T_FC2);
+    if (rc) return rc;
+  }
+  return ESMB200_OK;
+}
+
+
+int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const float* pos_table, const float* msa_pos,
+                      int32_t msa_pos_dim, const float* ln_weight, const float* ln_bias, float eps, float* x,
+                      int32_t B, int32_t R, int32_t C, int32_t E, int32_t padding_idx, void* stream) {
+  if (!tokens || !embed_table || !pos_table || !ln_weight || !ln_bias || !x) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || R <= 0 || C <= 0 || E <= 0 || E % 4 != 0 || E > 20 * 128) return fail(ESMB200_EINVAL, "bad shape");
+  if (msa_pos && msa_pos_dim != E && msa_pos_dim != 1)
+    return fail(ESMB200_EINVAL, "msa_position_embedding width must be E or 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(T_EMBED, st);
+  const size_t smem = (size_t)C * sizeof(int);
+  const int grid = B * R;
+  if (E <= 4 * 128)
+    msa_embed_kernel<4><<<grid, 256, smem, st>>>(tokens, embed_table, pos_table, msa_pos, msa_pos_dim, ln_weight,
+                                                  ln_bias, eps, x, R, C, E, padding_idx);
+  else if (E <= 10 * 128)
+    msa_embed_kernel<10><<<grid, 256, smem, st>>>(tokens, embed_table, pos_table, msa_pos, msa_pos_dim, ln_weight,
+                                                   ln_bias, eps, x, R, C, E, padding_idx);
+  else
+    msa_embed_kernel<20><<<grid, 256, smem, st>>>(tokens, embed_table, pos_table, msa_pos, msa_pos_dim, ln_weight,
+                                                   ln_bias, eps, x, R, C, E, padding_idx);
+  CK(cudaGetLastError());
   return ESMB200_OK;
 }
 

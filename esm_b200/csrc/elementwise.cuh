@@ -172,4 +172,96 @@ __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __
   for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
 }
 
+// MSA row attention: q is zeroed at padded positions before the logits are summed over the alignment rows
+// (/root/reference/esm/axial_attention.py:82-85).  qkv [M, 3E] fp16, pad [M] (1 = padding); one warp per row.
+__global__ void __launch_bounds__(256)
+zero_q_at_pads_kernel(__half* __restrict__ qkv, const uint8_t* __restrict__ pad, int M, int E) {
+  const int row = blockIdx.x * 8 + threadIdx.x / 32;
+  if (row >= M || !pad[row]) return;
+  uint4* q = reinterpret_cast<uint4*>(qkv + (size_t)row * 3 * E);  // E % 64 == 0: E*2 bytes is a multiple of 16
+  for (int i = threadIdx.x % 32; i < E / 8; i += 32) q[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// MSA Transformer embedding prologue (/root/reference/esm/model/msa_transformer.py:155-172): for every token of an
+// alignment row,  x = LayerNorm(embed_tokens[tok] + embed_positions[pos] + msa_position_embedding[r]) * (1 - is_pad),
+// pos = (number of non-pad tokens up to and including this one) + padding_idx for non-pad tokens, padding_idx for pads
+// (LearnedPositionalEmbedding.forward, /root/reference/esm/modules.py:241-257).  One block per alignment row.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+msa_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ embed_table,
+                 const float* __restrict__ pos_table, const float* __restrict__ msa_pos, int msa_dim,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ x,
+                 int R, int C, int E, int padding_idx) {
+  extern __shared__ int s_pos[];  // [C]
+  const int row = blockIdx.x;     // b * R + r
+  const int r = row % R;
+  const int64_t* tok = tokens + (size_t)row * C;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (warp == 0) {
+    int base = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      const bool nonpad = c < C && tok[c] != padding_idx;
+      const uint32_t bits = __ballot_sync(0xffffffffu, nonpad);
+      if (c < C) s_pos[c] = nonpad ? base + __popc(bits & (0xffffffffu >> (31 - lane))) + padding_idx : padding_idx;
+      base += __popc(bits);
+    }
+  }
+  __syncthreads();
+  const int nvec = E / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* m4 = (msa_pos && msa_dim == E) ? reinterpret_cast<const float4*>(msa_pos + (size_t)r * E) : nullptr;
+  const float m1 = (msa_pos && msa_dim == 1) ? msa_pos[r] : 0.f;
+  for (int c = warp; c < C; c += blockDim.x / 32) {
+    const int64_t t = tok[c];
+    const float4* e4 = reinterpret_cast<const float4*>(embed_table + (size_t)t * E);
+    const float4* p4 = reinterpret_cast<const float4*>(pos_table + (size_t)s_pos[c] * E);
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) {
+        const float4 a = __ldg(e4 + idx), b = __ldg(p4 + idx);
+        float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        if (m4) {
+          const float4 m = __ldg(m4 + idx);
+          o.x += m.x; o.y += m.y; o.z += m.z; o.w += m.w;
+        } else if (msa_pos) {
+          o.x += m1; o.y += m1; o.z += m1; o.w += m1;
+        }
+        v[i] = o;
+        s += (o.x + o.y) + (o.z + o.w);
+      }
+    }
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+    const float keep = t == padding_idx ? 0.f : 1.f;
+    float4* out = reinterpret_cast<float4*>(x + ((size_t)row * C + c) * E);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) {
+        const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+        float4 o;
+        o.x = ((v[i].x - mean) * rstd * g.x + b.x) * keep;
+        o.y = ((v[i].y - mean) * rstd * g.y + b.y) * keep;
+        o.z = ((v[i].z - mean) * rstd * g.z + b.z) * keep;
+        o.w = ((v[i].w - mean) * rstd * g.w + b.w) * keep;
+        out[idx] = o;
+      }
+    }
+  }
+}
+
 }  // namespace esmb200

@@ -28,7 +28,9 @@ struct TiedParams {
   float* S;            // [H, B, C, C] fp32 logits (tied_scores) / probabilities (tied_softmax, optional)
   __half* P;           // [H*B*C, Cp] fp16 probabilities
   __half* ctx;         // [B*R*C, E]
-  const uint8_t* key_pad;  // optional [B, C]: 1 = padded key column (filled with -10000 before the softmax)
+  const uint8_t* key_pad;  // optional: key_pad[b * key_pad_stride + c] = 1 <=> key column c of alignment b is padding
+                           // (filled with -10000 before the softmax)
+  long long key_pad_stride;
   int write_probs;     // tied_softmax: also write the fp32 probabilities over S
 };
 
@@ -164,7 +166,7 @@ tied_softmax_kernel(const TiedParams p) {
   if (row >= rows) return;
   const int b = (int)((row / p.C) % p.B);
   float* s = p.S + row * p.C;
-  const uint8_t* pad = p.key_pad ? p.key_pad + (size_t)b * p.C : nullptr;
+  const uint8_t* pad = p.key_pad ? p.key_pad + (size_t)b * p.key_pad_stride : nullptr;
   float v[TIED_MAX_C / 32];
   float mx = -INFINITY;
 #pragma unroll

@@ -27,8 +27,13 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+import ctypes
+from argparse import Namespace
+from typing import Dict, List, Sequence, Union
+
 from . import _lib
-from .model import _ptr, _stream
+from .alphabet import Alphabet
+from .model import ContactPredictionHead, RobertaLMHead, _ptr, _stream, _workspace
 
 
 class _AttnParams(nn.Module):
@@ -90,6 +95,61 @@ class AxialTransformerLayer(nn.Module):
         self.feed_forward_layer = _ResidualBlock(_FFNParams(embedding_dim, ffn_embedding_dim), embedding_dim)
         self._packed = None
         self._packed_key = None
+        self._handles = None
+        self._handles_key = None
+
+    # ---- C-ABI handles: (row attention-only layer, column attention + feed-forward layer) ----------------------
+    def handles(self):
+        ps = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._handles is not None and key == self._handles_key:
+            return self._handles
+        self.release()
+        for p in ps:
+            if not p.is_cuda:
+                raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: move the model with .cuda(); "
+                                        "there is no CPU fallback")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.Esmb200Error("esm_b200 expects contiguous fp32 master parameters")
+        lib = _lib.load()
+
+        def create(attn_blk: _ResidualBlock, ffn_blk: Optional[_ResidualBlock]):
+            a = attn_blk.layer
+            w = _lib.LayerWeights()
+            w.embed_dim, w.num_heads, w.ffn_dim = self.embedding_dim, self.num_heads, self.ffn_embedding_dim
+            w.ln_eps = attn_blk.layer_norm.eps
+            w.ln1_weight, w.ln1_bias = attn_blk.layer_norm.weight.data_ptr(), attn_blk.layer_norm.bias.data_ptr()
+            for n in ("q", "k", "v", "out"):
+                lin = getattr(a, n + "_proj")
+                setattr(w, n + "_weight", lin.weight.data_ptr())
+                setattr(w, n + "_bias", lin.bias.data_ptr())
+            if ffn_blk is not None:
+                f = ffn_blk.layer
+                w.ln2_weight, w.ln2_bias = ffn_blk.layer_norm.weight.data_ptr(), ffn_blk.layer_norm.bias.data_ptr()
+                w.fc1_weight, w.fc1_bias = f.fc1.weight.data_ptr(), f.fc1.bias.data_ptr()
+                w.fc2_weight, w.fc2_bias = f.fc2.weight.data_ptr(), f.fc2.bias.data_ptr()
+            out = ctypes.c_void_p()
+            with torch.cuda.device(ps[0].device):
+                _lib.check(lib.esmb200_layer_create(ctypes.byref(w), _stream(), ctypes.byref(out)))
+            return out
+
+        row = create(self.row_self_attention, None)
+        col = create(self.column_self_attention, self.feed_forward_layer)
+        self._handles, self._handles_key = (row, col), key
+        return self._handles
+
+    def release(self):
+        if self._handles is not None:
+            lib = _lib.load()
+            for h in self._handles:
+                lib.esmb200_layer_destroy(h)
+            self._handles, self._handles_key = None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     # ---- fp16 operand copies (re-made when a parameter changes) ------------------------------------------------
     def _pack(self):
@@ -132,7 +192,11 @@ class AxialTransformerLayer(nn.Module):
                             need_probs: bool = False):
         """In-place layer on the batch-major residual stream xb [B,R,C,E] fp32 (what MSATransformer keeps between
         layers).  padding_mask [B,R,C] bool or None.  Returns (row_attn [H,B,C,C], column_attn [H,C,B,R,R]) or
-        (None, None)."""
+        (None, None).  Without attention maps this is one esmb200_axial_stack_forward call; with them the sub-layers
+        are driven one C-ABI call at a time so that the column-attention maps can be produced too."""
+        if not need_probs:
+            run_axial_stack([self], xb, padding_mask)
+            return None, None
         lib = _lib.load()
         B, R, C, E = xb.shape
         H, d, Fd = self.num_heads, 64, self.ffn_embedding_dim
@@ -194,3 +258,175 @@ class AxialTransformerLayer(nn.Module):
             # reference shapes: column_attn [H, C, B, R, R] (axial_attention.py:206), row_attn [H, B, C, C] (:87)
             col_probs = col_probs.view(B, C, H, R, R).permute(2, 1, 0, 3, 4).contiguous()
         return row_probs, col_probs
+
+
+def run_axial_stack(layers: Sequence[AxialTransformerLayer], xb: torch.Tensor,
+                    padding_mask: Optional[torch.Tensor] = None, row_attn_layers: Sequence[int] = ()):
+    """esmb200_axial_stack_forward on xb [B,R,C,E] fp32 in place (msa_transformer.py:190-201's loop).
+    Returns {layer index: row attention [H,B,C,C] fp32} for the indices in row_attn_layers."""
+    if not xb.is_cuda:
+        raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    assert xb.dtype == torch.float32 and xb.is_contiguous()
+    lib = _lib.load()
+    B, R, C, E = xb.shape
+    n = len(layers)
+    Fd, H = layers[0].ffn_embedding_dim, layers[0].num_heads
+    dev = xb.device
+    with torch.cuda.device(dev):
+        hs = [l.handles() for l in layers]
+        rows = (ctypes.c_void_p * n)(*[h[0] for h in hs])
+        cols = (ctypes.c_void_p * n)(*[h[1] for h in hs])
+        nbytes = lib.esmb200_axial_workspace_bytes(E, Fd, B, R, C)
+        ws = _workspace(nbytes, dev)
+        pm = cm = None
+        if padding_mask is not None:
+            pm = padding_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            assert pm.shape == (B, R, C)
+            cm = pm.permute(0, 2, 1).contiguous()
+        attns = (ctypes.c_void_p * n)()
+        out = {}
+        for i in row_attn_layers:
+            out[i] = torch.empty((H, B, C, C), dtype=torch.float32, device=dev)
+            attns[i] = out[i].data_ptr()
+        _lib.check(lib.esmb200_axial_stack_forward(rows, cols, n, _ptr(xb), _ptr(pm), _ptr(cm), B, R, C,
+                                                   attns if row_attn_layers else None, _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+class LearnedPositionalEmbedding(nn.Embedding):
+    """Parameter container with the reference's shape (modules.py:224-239: max_positions + padding_idx + 1 rows);
+    the lookup itself is part of esmb200_msa_embed."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, padding_idx: int):
+        super().__init__(num_embeddings + padding_idx + 1, embedding_dim, padding_idx)
+        self.max_positions = num_embeddings
+
+
+class MSATransformer(nn.Module):
+    """Drop-in for esm.model.msa_transformer.MSATransformer (msa_transformer.py:20-238) at inference: same
+    constructor (`args` namespace + alphabet), same state-dict keys, same forward contract
+    `model(tokens [B,R,C], repr_layers, need_head_weights, return_contacts)` -> dict with `logits`,
+    `representations`, and — when asked — `row_attentions`, `col_attentions`, `contacts`.
+
+    Deviation: `return_contacts=True` alone returns `row_attentions` and `contacts` but not `col_attentions` (the
+    reference materialises the [B,L,H,C,R,R] column maps as a side effect, 4.8 GB for a 128 x 512 MSA); pass
+    `need_head_weights=True` to get them."""
+
+    def __init__(self, args: Union[Namespace, dict, None] = None, alphabet: Union[Alphabet, str] = "MSA Transformer",
+                 **kwargs):
+        super().__init__()
+        if args is None:
+            args = Namespace(**kwargs)
+        elif isinstance(args, dict):
+            args = Namespace(**args)
+        defaults = dict(layers=12, embed_dim=768, ffn_embed_dim=3072, attention_heads=12, max_positions=1024,
+                        embed_positions_msa=True)
+        for k, v in defaults.items():
+            if not hasattr(args, k):
+                setattr(args, k, v)
+        self.args = args
+        if isinstance(alphabet, str):
+            alphabet = Alphabet.from_architecture(alphabet)
+        self.alphabet = alphabet
+        self.alphabet_size = len(alphabet)
+        self.padding_idx = alphabet.padding_idx
+        self.mask_idx = alphabet.mask_idx
+        self.cls_idx = alphabet.cls_idx
+        self.eos_idx = alphabet.eos_idx
+        self.prepend_bos = alphabet.prepend_bos
+        self.append_eos = alphabet.append_eos
+        E = args.embed_dim
+        self.embed_tokens = nn.Embedding(self.alphabet_size, E, padding_idx=self.padding_idx)
+        if getattr(args, "embed_positions_msa", False):
+            emb_dim = getattr(args, "embed_positions_msa_dim", E)
+            self.msa_position_embedding = nn.Parameter(0.01 * torch.randn(1, 1024, 1, emb_dim))
+        else:
+            self.register_parameter("msa_position_embedding", None)
+        self.layers = nn.ModuleList([AxialTransformerLayer(E, args.ffn_embed_dim, args.attention_heads)
+                                     for _ in range(args.layers)])
+        self.contact_head = ContactPredictionHead(args.layers * args.attention_heads, self.prepend_bos,
+                                                  self.append_eos, eos_idx=self.eos_idx)
+        self.embed_positions = LearnedPositionalEmbedding(args.max_positions, E, self.padding_idx)
+        self.emb_layer_norm_before = nn.LayerNorm(E)
+        self.emb_layer_norm_after = nn.LayerNorm(E)
+        self.lm_head = RobertaLMHead(embed_dim=E, output_dim=self.alphabet_size, weight=self.embed_tokens.weight)
+
+    @property
+    def num_layers(self) -> int:
+        return self.args.layers
+
+    def max_tokens_per_msa_(self, value: int) -> None:
+        """Accepted for API compatibility (msa_transformer.py:228-238): the reference chunks its attention above
+        `max_tokens_per_msa` to bound memory; the kernels here never materialise per-row score tensors."""
+
+    @torch.no_grad()
+    def forward(self, tokens, repr_layers=[], need_head_weights=False, return_contacts=False):
+        assert tokens.ndim == 3
+        if not tokens.is_cuda:
+            raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: pass tokens.cuda(); no CPU fallback")
+        lib = _lib.load()
+        tokens = tokens.contiguous()
+        B, R, C = tokens.shape
+        E, N, H = self.args.embed_dim, self.args.layers, self.args.attention_heads
+        if C > self.embed_positions.max_positions:  # modules.py:243-247
+            raise ValueError(f"Sequence length {C} above maximum  sequence length of {self.embed_positions.max_positions}")
+        mp = self.msa_position_embedding
+        if mp is not None and R > 1024:           # msa_transformer.py:158-163
+            raise RuntimeError("Using model with MSA position embedding trained on maximum MSA "
+                               f"depth of 1024, but received {R} alignments.")
+        padding_mask = tokens.eq(self.padding_idx)  # B, R, C
+        if not bool(padding_mask.any()):            # msa_transformer.py:152-153
+            padding_mask = None
+        repr_layers = set(repr_layers)
+        hidden: Dict[int, torch.Tensor] = {}
+        want_rows = need_head_weights or return_contacts
+        dev = tokens.device
+        with torch.cuda.device(dev):
+            x = torch.empty((B, R, C, E), dtype=torch.float32, device=dev)
+            ln = self.emb_layer_norm_before
+            _lib.check(lib.esmb200_msa_embed(_ptr(tokens), _ptr(self.embed_tokens.weight),
+                                             _ptr(self.embed_positions.weight), _ptr(mp),
+                                             mp.shape[-1] if mp is not None else 0, _ptr(ln.weight), _ptr(ln.bias),
+                                             ln.eps, _ptr(x), B, R, C, E, self.padding_idx, _stream()))
+            if 0 in repr_layers:
+                hidden[0] = x.clone()
+            row_attn: Dict[int, torch.Tensor] = {}
+            col_attn: List[torch.Tensor] = []
+            if need_head_weights:   # both kinds of attention maps: one sub-layer call at a time
+                for i, layer in enumerate(self.layers):
+                    rp, cp = layer.forward_batch_major(x, padding_mask, need_probs=True)
+                    row_attn[i] = rp
+                    col_attn.append(cp.permute(2, 0, 1, 3, 4))           # H,C,B,R,R -> B,H,C,R,R
+                    if (i + 1) in repr_layers and i + 1 < N:
+                        hidden[i + 1] = x.clone()
+            else:                   # whole segments of the stack per C-ABI call
+                stops = sorted({i for i in repr_layers if 0 < i < N} | {N})
+                start = 0
+                for stop in stops:
+                    idx = list(range(start, stop))
+                    got = run_axial_stack([self.layers[i] for i in idx], x, padding_mask,
+                                          list(range(len(idx))) if want_rows else ())
+                    for k, t in got.items():
+                        row_attn[start + k] = t
+                    if stop < N:
+                        hidden[stop] = x.clone()
+                    start = stop
+            ln = self.emb_layer_norm_after
+            logits = self.lm_head.forward_native(x.view(B, R * C, E), ln.weight, ln.bias, ln.eps).view(B, R, C, -1)
+            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(ln.weight), _ptr(ln.bias), _ptr(x), B * R * C, E, ln.eps,
+                                             _stream()))
+        if N in repr_layers:
+            hidden[N] = x  # the last representation is post-LayerNorm (msa_transformer.py:204-209)
+        result = {"logits": logits, "representations": hidden}
+        if want_rows:
+            # H,B,C,C per layer -> B,L,H,C,C (msa_transformer.py:196-197,215)
+            row_attentions = torch.stack([row_attn[i].permute(1, 0, 2, 3) for i in range(N)], 1)
+            result["row_attentions"] = row_attentions
+            if need_head_weights:
+                result["col_attentions"] = torch.stack(col_attn, 1)  # B,L,H,C,R,R
+            if return_contacts:
+                result["contacts"] = self.contact_head(tokens, row_attentions)
+        return result
+
+    def predict_contacts(self, tokens):
+        return self(tokens, return_contacts=True)["contacts"]

@@ -15,6 +15,8 @@ from typing import Optional, Tuple
 
 import torch
 
+from argparse import Namespace
+
 from .alphabet import Alphabet
 from .model import ESM2
 
@@ -96,3 +98,68 @@ def esm2_t30_150M_UR50D():
 
 def esm2_t48_15B_UR50D():
     return load_model_and_alphabet("esm2_t48_15B_UR50D")
+
+
+# ---- MSA Transformer (pretrained.py:104-125, 293-300) -----------------------------------------------------------
+MSA_ARCH = {  # name -> constructor arguments (the checkpoints' args)
+    "esm_msa1_t12_100M_UR50S": dict(layers=12, embed_dim=768, ffn_embed_dim=3072, attention_heads=12,
+                                    max_positions=1024, embed_positions_msa=True),
+    "esm_msa1b_t12_100M_UR50S": dict(layers=12, embed_dim=768, ffn_embed_dim=3072, attention_heads=12,
+                                     max_positions=1024, embed_positions_msa=True),
+}
+
+
+def _upgrade_msa_checkpoint(data):
+    """pretrained.py:110-123: strip the fairseq "encoder." / "sentence_encoder." prefixes from argument and parameter
+    names, swap "row" <-> "column" in parameter names (the checkpoints were trained with the two attention blocks
+    named the other way round), and take the width of msa_position_embedding from the tensor (1 in the first release)."""
+    strip_arg = lambda k: "".join(k.split("encoder_")[1:]) if "encoder" in k else k
+    strip1 = lambda k: "".join(k.split("encoder.")[1:]) if "encoder" in k else k
+    strip2 = lambda k: "".join(k.split("sentence_encoder.")[1:]) if "sentence_encoder" in k else k
+    swap = lambda k: k.replace("row", "column") if "row" in k else k.replace("column", "row")
+    args = {strip_arg(k): v for k, v in vars(data["args"]).items()}
+    state = {strip1(strip2(swap(k))): v for k, v in data["model"].items()}
+    if args.get("embed_positions_msa", False):
+        args["embed_positions_msa_dim"] = state["msa_position_embedding"].size(-1)
+    return args, state
+
+
+def load_msa_model_and_alphabet_local(model_location: str):
+    from .msa import MSATransformer
+    data = torch.load(str(model_location), map_location="cpu", weights_only=False)
+    reg = str(model_location)[:-3] + "-contact-regression.pt"
+    has_reg = os.path.exists(reg)
+    if has_reg:
+        data["model"].update(torch.load(reg, map_location="cpu", weights_only=False)["model"])
+    args, state = _upgrade_msa_checkpoint(data)
+    alphabet = Alphabet.from_architecture("msa_transformer")
+    model = MSATransformer(Namespace(**args), alphabet)
+    model.load_state_dict(state, strict=has_reg)
+    model.random_init = False
+    return model.eval(), alphabet
+
+
+def load_msa_model_and_alphabet(model_name: str, seed: int = 0):
+    from .msa import MSATransformer
+    if model_name.endswith(".pt"):
+        return load_msa_model_and_alphabet_local(model_name)
+    if model_name not in MSA_ARCH:
+        raise ValueError(f"unknown MSA Transformer model {model_name!r}")
+    path = _hub_path(model_name)
+    if os.path.exists(path):
+        return load_msa_model_and_alphabet_local(path)
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    alphabet = Alphabet.from_architecture("msa_transformer")
+    model = MSATransformer(Namespace(**MSA_ARCH[model_name]), alphabet)
+    torch.random.set_rng_state(gen_state)
+    model.random_init = True
+    return model.eval(), alphabet
+
+
+def esm_msa1_t12_100M_UR50S():
+    return load_msa_model_and_alphabet("esm_msa1_t12_100M_UR50S")
+
+
+def esm_msa1b_t12_100M_UR50S():
+    return load_msa_model_and_alphabet("esm_msa1b_t12_100M_UR50S")

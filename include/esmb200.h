@@ -58,7 +58,7 @@ typedef struct esmb200_layer_weights {
   const float* out_bias;
   const float* ln2_weight; /* final_layer_norm.weight [E] */
   const float* ln2_bias;
-  const float* fc1_weight; /* fc1.weight [F,E] */
+  const float* fc1_weight; /* fc1.weight [F,E]; NULL = attention-only layer (no ln2/fc1/fc2; esmb200_axial_stack_forward) */
   const float* fc1_bias;   /* fc1.bias   [F]   */
   const float* fc2_weight; /* fc2.weight [E,F] */
   const float* fc2_bias;   /* fc2.bias   [E]   */
@@ -151,6 +151,30 @@ int esmb200_tied_row_attention(const void* qkv_f16, const uint8_t* key_pad, void
                                int32_t R, int32_t C, int32_t H, void* scratch, size_t scratch_bytes, void* stream);
 int esmb200_column_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, int32_t B, int32_t R,
                              int32_t C, int32_t H, void* scratch, void* stream);
+
+/* n_layers x AxialTransformerLayer.forward (esm/modules.py:195-221) = the layer loop of MSATransformer.forward
+ * (esm/model/msa_transformer.py:190-201), in place on the batch-major residual stream x [B,R,C,E] fp32:
+ *   x += out_proj(tied_row_attention(LN(x)));  x += out_proj(column_attention(LN(x)));  x += fc2(gelu(fc1(LN(x))))
+ * row_layers[i]: an esmb200_layer created with fc1_weight == NULL (attention-only) from row_self_attention's
+ *   layer_norm + q/k/v/out projections; col_layers[i]: column_self_attention's layer_norm + projections as ln1/q/k/v/out
+ *   and feed_forward_layer's layer_norm + fc1/fc2 as ln2/fc1/fc2.
+ * pad_mask [B,R,C] and col_pad_mask [B,C,R] (its transpose): 1 = padding, both NULL for unpadded alignments.
+ * row_attn_out: NULL, or n_layers pointers (NULL entries allowed) to fp32 [H,B,C,C] buffers (the reference's
+ *   row-attention return layout, axial_attention.py:87,105). Column attention maps are not produced by this call.
+ * workspace: esmb200_axial_workspace_bytes(E,F,B,R,C) bytes. */
+size_t esmb200_axial_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t R, int32_t C);
+int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer* const* col_layers, int32_t n_layers,
+                                float* x, const uint8_t* pad_mask, const uint8_t* col_pad_mask, int32_t B, int32_t R,
+                                int32_t C, float* const* row_attn_out, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* MSA Transformer embedding prologue, esm/model/msa_transformer.py:155-172 (+ LearnedPositionalEmbedding.forward,
+ * esm/modules.py:241-257): x[B,R,C,E] fp32 = LayerNorm(embed_tokens[tok] + embed_positions[pos] +
+ * msa_position_embedding[r]) * (1 - is_pad). tokens int64 [B,R,C]; pos_table [max_positions + padding_idx + 1, E];
+ * msa_pos [>=R, msa_pos_dim] or NULL, msa_pos_dim = E or 1 (the initial esm_msa1 release, pretrained.py:123-125). */
+int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const float* pos_table, const float* msa_pos,
+                      int32_t msa_pos_dim, const float* ln_weight, const float* ln_bias, float eps, float* x,
+                      int32_t B, int32_t R, int32_t C, int32_t E, int32_t padding_idx, void* stream);
 
 /* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,

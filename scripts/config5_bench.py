@@ -38,6 +38,40 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     res = {"config": "12 x AxialTransformerLayer, MSA 128 x 512, E=768 H=12 (random init)", "ms_per_msa": round(ms, 3),
            "msa_per_s": round(1e3 / ms, 2), "TFLOP/s": round(flops / ms / 1e9, 1), "finite": bool(torch.isfinite(y).all())}
+    # the whole model (embedding prologue, 12 layers, final LayerNorm, LM head) on tokens (1, 128, 512)
+    from esm_b200 import pretrained
+    from oracle.msa_oracle import make_msa_tokens
+    model, _ = pretrained.esm_msa1b_t12_100M_UR50S()
+    model = model.cuda()
+    tokens = make_msa_tokens(1, R, C, seed=1234).cuda()
+    for _ in range(2):
+        out = model(tokens, repr_layers=[12])
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        out = model(tokens, repr_layers=[12])
+    b.record()
+    torch.cuda.synchronize()
+    res["model_forward_ms_per_msa"] = round(a.elapsed_time(b) / n, 3)
+    from esm_b200.msa import run_axial_stack
+    xs = x.clone()
+    run_axial_stack(layers, xs)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        run_axial_stack(layers, xs)  # one esmb200_axial_stack_forward call for the 12 layers
+    b.record()
+    torch.cuda.synchronize()
+    res["stack_single_call_ms_per_msa"] = round(a.elapsed_time(b) / n, 3)
+    for _ in range(2):
+        out = model(tokens, return_contacts=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        out = model(tokens, return_contacts=True)
+    b.record()
+    torch.cuda.synchronize()
+    res["model_forward_with_contacts_ms_per_msa"] = round(a.elapsed_time(b) / n, 3)
     # where the time goes: torch profiler, top CUDA kernels of one forward
     try:
         from torch.profiler import ProfilerActivity, profile

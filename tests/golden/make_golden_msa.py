@@ -1,5 +1,6 @@
-"""Generates tests/golden/msa_*.pt by running the UNMODIFIED reference esm.modules.AxialTransformerLayer
-(/root/reference) on the deterministic weights of oracle/msa_oracle.py::make_axial_state_dict.
+"""Generates tests/golden/msa_*.pt by running the UNMODIFIED reference esm.modules.AxialTransformerLayer and
+esm.model.msa_transformer.MSATransformer (/root/reference) on the deterministic weights of
+oracle/msa_oracle.py::make_axial_state_dict / make_msa_state_dict.
 Run in the build container only:  python tests/golden/make_golden_msa.py"""
 import os
 import sys
@@ -12,7 +13,39 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from esm.modules import AxialTransformerLayer  # noqa: E402  (the reference)
-from oracle.msa_oracle import make_axial_state_dict  # noqa: E402
+from argparse import Namespace  # noqa: E402
+
+import esm  # noqa: E402  (the reference)
+from oracle.msa_oracle import make_axial_state_dict, make_msa_state_dict, make_msa_tokens  # noqa: E402
+
+MODEL_CASES = {  # name: (layers, E, F, H, B, R, C, pad_cols, pad_rows_last, max_tokens_per_msa)
+    "msa_model_L2_E128_H2": (2, 128, 512, 2, 2, 5, 24, 3, 2, 2 ** 14),
+    "msa_model_L3_E256_H4_nopad": (3, 256, 1024, 4, 1, 9, 70, 0, 0, 2 ** 8),  # chunked reference path
+}
+
+
+def model_cases():
+    for name, (L, E, Fd, H, B, R, C, pc, pr, mt) in MODEL_CASES.items():
+        sd = make_msa_state_dict(L, E, Fd, H, seed=0)
+        alphabet = esm.data.Alphabet.from_architecture("msa_transformer")
+        args = Namespace(layers=L, embed_dim=E, ffn_embed_dim=Fd, attention_heads=H, dropout=0.0, attention_dropout=0.0,
+                         activation_dropout=0.0, max_tokens_per_msa=mt, max_tokens=mt, max_positions=1024,
+                         embed_positions_msa=True)
+        model = esm.MSATransformer(args, alphabet).eval()
+        model.load_state_dict(sd, strict=True)
+        tokens = make_msa_tokens(B, R, C, seed=1234, pad_cols=pc, pad_rows_last=pr)
+        with torch.no_grad():
+            out = model(tokens, repr_layers=[0, 1, L], return_contacts=True)
+        fx = {"config": {"layers": L, "E": E, "F": Fd, "H": H, "seed": 0, "B": B, "R": R, "C": C, "tok_seed": 1234,
+                         "pad_cols": pc, "pad_rows_last": pr},
+              "tokens": tokens, "logits": out["logits"].clone(),
+              "representations": {k: v.clone() for k, v in out["representations"].items()},
+              "row_attentions": out["row_attentions"].clone(), "contacts": out["contacts"].clone(),
+              "col_attentions_sample": out["col_attentions"][:, :, :, :3].clone(),
+              "reference": "facebookresearch/esm @ 2b36991 esm.MSATransformer, torch %s CPU fp32" % torch.__version__}
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(fx, path)
+        print(name, os.path.getsize(path) // 1024, "KiB")
 
 CASES = {  # name: (E, F, H, B, R, C, padded, max_tokens_per_msa)
     "msa_small_E128_H2": (128, 512, 2, 2, 6, 20, True, 2 ** 14),
@@ -49,3 +82,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    model_cases()

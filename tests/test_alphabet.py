@@ -1,5 +1,5 @@
 """CPU: known-answer token vectors from the reference's own tests (/root/reference/tests/test_alphabet.py:17-23,
-38-44) — the only offline golden vectors the reference holds for this path's inputs."""
+38-44, 62-86) — the only offline golden vectors the reference holds for this path's inputs."""
 import torch
 
 from esm_b200.alphabet import Alphabet
@@ -46,3 +46,27 @@ def test_unknown_symbol_raises_like_reference():
     except KeyError:
         return
     raise AssertionError("expected KeyError for a symbol outside the vocabulary")
+
+
+def test_msa_transformer_golden_tokens():
+    """/root/reference/tests/test_alphabet.py:62-86 (esm_msa1b alphabet: <cls> prepended, no <eos>, tokens [1, R, C])."""
+    a = Alphabet.from_architecture("MSA Transformer")
+    assert a.prepend_bos and not a.append_eos and a.use_msa and len(a) == 33
+    data = [("protein1", "MKTVRQG"), ("protein2", "KALTRAI"), ("protein3", "KAAISQQ")]
+    labels, strs, toks = a.get_batch_converter()(data)
+    expected = torch.tensor([[[0, 20, 15, 11, 7, 10, 16, 6], [0, 15, 5, 4, 11, 10, 5, 12], [0, 15, 5, 5, 12, 8, 16, 16]]])
+    assert torch.equal(toks, expected)
+    assert labels == [["protein1", "protein2", "protein3"]]
+
+
+def test_msa_batch_converter_pads_rows_and_columns():
+    a = Alphabet.from_architecture("msa_transformer")
+    batch = [[("a", "MKT"), ("b", "MRT")], [("c", "MKTVR")]]
+    _, _, toks = a.get_batch_converter()(batch)
+    assert toks.shape == (2, 2, 6)
+    assert toks[0, 0].tolist() == [0, 20, 15, 11, 1, 1] and toks[1, 1].tolist() == [1] * 6
+    try:
+        a.get_batch_converter()([("a", "MKT"), ("b", "MK")])
+    except RuntimeError:
+        return
+    raise AssertionError("unaligned MSA must raise like the reference")

@@ -83,3 +83,58 @@ def test_axial_layer_ragged_shapes_against_oracle(B, R, C):
     assert rel_fro(out2.permute(2, 0, 1, 3).cpu(), ref) <= 3e-3
     assert float((row.cpu() - row_ref).abs().max()) <= 1e-2
     assert float((col.cpu() - col_ref).abs().max()) <= 1e-2
+
+
+def build_model(cfg):
+    from argparse import Namespace
+    from esm_b200.msa import MSATransformer
+    from oracle.msa_oracle import make_msa_state_dict
+    sd = make_msa_state_dict(cfg["layers"], cfg["E"], cfg["F"], cfg["H"], seed=cfg["seed"])
+    model = MSATransformer(Namespace(layers=cfg["layers"], embed_dim=cfg["E"], ffn_embed_dim=cfg["F"],
+                                     attention_heads=cfg["H"], max_positions=1024, embed_positions_msa=True))
+    model.load_state_dict(sd, strict=True)
+    return model.eval().cuda(), sd
+
+
+@pytest.mark.parametrize("name", ["msa_model_L2_E128_H2", "msa_model_L3_E256_H4_nopad"])
+def test_msa_transformer_against_reference_golden(name, golden_dir):
+    """esm_b200.msa.MSATransformer (embedding prologue kernel, esmb200_axial_stack_forward, LM head, contact head)
+    against the reference's MSATransformer outputs; padding positions are not compared (see msa.py)."""
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg, tokens = fx["config"], fx["tokens"]
+    model, _ = build_model(cfg)
+    keep = tokens.ne(1)
+    L = cfg["layers"]
+    out = model(tokens.cuda(), repr_layers=[0, 1, L], return_contacts=True)
+    assert "col_attentions" not in out
+    for k, v in fx["representations"].items():
+        assert rel_fro(out["representations"][k].cpu()[keep], v[keep]) <= (1e-5 if k == 0 else 3e-3), k
+    assert rel_fro(out["logits"].cpu()[keep], fx["logits"][keep]) <= 4e-3
+    assert float((out["row_attentions"].cpu() - fx["row_attentions"]).abs().max()) <= 1e-2
+    assert float((out["contacts"].cpu() - fx["contacts"]).abs().max()) <= 1e-2
+    # plain forward (no attention maps): one esmb200_axial_stack_forward call for the whole stack
+    out2 = model(tokens.cuda(), repr_layers=[L])
+    assert set(out2.keys()) == {"logits", "representations"}
+    assert rel_fro(out2["representations"][L].cpu()[keep], fx["representations"][L][keep]) <= 3e-3
+    # need_head_weights: column maps too, B x L x H x C x R x R
+    out3 = model(tokens.cuda(), need_head_weights=True)
+    col = out3["col_attentions"][:, :, :, :3].cpu()
+    qkeep = keep[:, :, :3].permute(0, 2, 1)                      # [B, 3, R] query rows that are not padding
+    diff = (col - fx["col_attentions_sample"]).abs()             # [B, L, H, 3, R, R]
+    assert float(diff.permute(0, 3, 4, 1, 2, 5)[qkeep].max()) <= 1e-2
+    assert float((out3["row_attentions"].cpu() - fx["row_attentions"]).abs().max()) <= 1e-2
+
+
+def test_msa_factory_and_batch_converter_end_to_end():
+    """esm_b200.pretrained.esm_msa1b_t12_100M_UR50S() -> (model, alphabet) like the reference's factory; a small MSA
+    through the batch converter; contacts [B, C-1, C-1] symmetric in (0, 1)."""
+    from esm_b200 import pretrained
+    model, alphabet = pretrained.esm_msa1b_t12_100M_UR50S()
+    model = model.cuda()
+    msa = [("s%d" % i, "MKTVRQERLKSIVRILERSKEPVSGAQLAEELSVSRQVIVQDIAYLRSLGYNIVATPRGYVLAGG"[:40]) for i in range(6)]
+    _, _, tokens = alphabet.get_batch_converter()(msa)
+    assert tokens.shape == (1, 6, 41)
+    contacts = model.predict_contacts(tokens.cuda())
+    assert contacts.shape == (1, 40, 40)
+    assert torch.isfinite(contacts).all() and float(contacts.min()) >= 0 and float(contacts.max()) <= 1
+    assert float((contacts - contacts.transpose(1, 2)).abs().max()) <= 1e-6
