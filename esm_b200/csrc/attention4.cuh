@@ -240,16 +240,30 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
 
         float rsum = 0.f;
+#ifdef ESMB200_ATTN_X_SKIPALL  // experiment: the softmax warps only do the barrier handshake
+        for (int trip = 0; trip < 0; ++trip) {
+#else
         for (int trip = 0;; ++trip) {
+#endif
           // ---- p = exp(s - m_ref) for the 64 keys of this block -> fp16 P buffer; row sum; block max
           const float mneg = -m_ref * LOG2E;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           uint32_t sv[2][32];
+#ifdef ESMB200_ATTN_X_NOLD  // experiment: no TMEM read of S (values made up from the loop counters)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            sv[0][i] = (__float_as_uint(m_ref) & 0x3fffffffu) ^ (uint32_t)(i << 12) ^ g;
+            sv[1][i] = (__float_as_uint(m_ref) & 0x3fffffffu) ^ (uint32_t)(i << 11) ^ g;
+          }
+          reg_fence(sv[0]);
+          reg_fence(sv[1]);
+#else
           tmem_ld_32x32b_x32(ts, sv[0]);
           tmem_ld_32x32b_x32(ts + 32, sv[1]);
           tmem_wait_ld_dep(sv[0]);  // ONE tcgen05.wait::ld retires both loads (each extra wait slows the MMA pipe)
           reg_fence(sv[1]);
+#endif
           if (warp == 2 && lane == 0) ATRACE(7, g);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -260,8 +274,13 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
               for (int i = 0; i < 16; ++i) {
                 const float s0 = __uint_as_float(sv[c][2 * i]), s1 = __uint_as_float(sv[c][2 * i + 1]);
                 mx[i & 3] = fmaxf(mx[i & 3], fmaxf(s0, s1));
+#ifdef ESMB200_ATTN_X_NOEXP  // experiment: no MUFU work
+                const float p0 = fmaf(s0, LOG2E, mneg);
+                const float p1 = fmaf(s1, LOG2E, mneg);
+#else
                 const float p0 = ex2_approx(fmaf(s0, LOG2E, mneg));
                 const float p1 = ex2_approx(fmaf(s1, LOG2E, mneg));
+#endif
                 sum[i & 3] += p0 + p1;
                 pk[i] = pack_half2(p0, p1);
               }
@@ -278,7 +297,11 @@ attention_fwd_kernel_v4(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 pk[i] = pack_half2(p0, p1);
               }
             }
+#ifdef ESMB200_ATTN_X_NOST  // experiment: P is not written
+            reg_fence16(pk);
+#else
             tmem_st_32x32b_x16(tp + c * 16, pk);
+#endif
           }
           rsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
           if (j == 0 || trip == 1) break;

@@ -249,6 +249,10 @@ __device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[32]) {
 // Compiler-only fence: makes r[] look (re)defined here without emitting an instruction. Used after ONE
 // tcgen05.wait::ld that retires several in-flight tcgen05.ld: the wait carries the dependency for its own operand
 // array, this pins the other arrays behind it.
+__device__ __forceinline__ void reg_fence16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
 __device__ __forceinline__ void reg_fence(uint32_t (&r)[32]) {
   asm volatile(""
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
