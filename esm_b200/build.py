@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libesmb200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "gemm2.cuh", "attention.cuh", "attention2.cuh", "attention3.cuh", "attention4.cuh", "attention5.cuh", "tied_attention.cuh", "elementwise.cuh", os.path.join("..", "..", "include", "esmb200.h")]
+HEADERS = ["common.cuh", "gemm.cuh", "gemm2.cuh", "attention.cuh", "attention2.cuh", "attention3.cuh", "attention4.cuh", "attention5.cuh", "attention7.cuh", "tied_attention.cuh", "elementwise.cuh", os.path.join("..", "..", "include", "esmb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

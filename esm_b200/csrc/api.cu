@@ -21,6 +21,7 @@
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention5.cuh"
+#include "attention7.cuh"
 #include "tied_attention.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
@@ -144,7 +145,7 @@ int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 4;
+    v = (e && e[0] >= '1' && e[0] <= '7') ? (e[0] - '0') : 4;
   }
   return v;
 }
@@ -271,7 +272,8 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
       CUtensorMap tkv;
       rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn3_cfg::BLOCK_KV);
       if (rc) return rc;
-      e = attn_version() == 5   ? launch_attention_v5(tq, tkv, ap, num_sms(), st)
+      e = attn_version() == 7   ? launch_attention_v7(tq, tkv, ap, num_sms(), st)
+          : attn_version() == 5 ? launch_attention_v5(tq, tkv, ap, num_sms(), st)
           : attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st)
                                 : launch_attention_v3(tq, tkv, ap, st);
     } else {
