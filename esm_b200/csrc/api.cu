@@ -139,13 +139,13 @@ int gemm_version() {
   return v;
 }
 
-// attention implementation: 4 = attention4.cuh (persistent, default); 5 = + TMEM lookahead (measured slower);
-// 3 / 2 / 1 = earlier kernels, all kept for A/B runs
+// attention implementation: 7 = attention7.cuh (persistent, two MMA issuing threads, default); 4 = attention4.cuh
+// (persistent, one issuing thread); 5 = 4 + TMEM lookahead (measured slower); 3 / 2 / 1 = earlier kernels (A/B runs)
 int attn_version() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] >= '1' && e[0] <= '7') ? (e[0] - '0') : 4;
+    v = (e && e[0] >= '1' && e[0] <= '7' && e[0] != '6') ? (e[0] - '0') : 7;
   }
   return v;
 }
@@ -718,7 +718,8 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
   cudaError_t e;
   {
     ProfScope ps(T_ATTN, st);
-    e = launch_attention_v4(tq, tkv, ap, num_sms(), st);
+    e = attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st)
+                            : launch_attention_v7(tq, tkv, ap, num_sms(), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
   return ESMB200_OK;
@@ -810,7 +811,8 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
       ap.keybits = ws.as.keybits; ap.kvlen = ws.as.kvlen; ap.words = ws.as.words;
       ap.ctx = ws.ctx; ap.row_max = nullptr; ap.row_sum = nullptr; ap.cols = C;
       ProfScope ps(T_ATTN, st);
-      e = launch_attention_v4(tcq, tckv, ap, num_sms(), st);
+      e = attn_version() == 4 ? launch_attention_v4(tcq, tckv, ap, num_sms(), st)
+                              : launch_attention_v7(tcq, tckv, ap, num_sms(), st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
     memset(&g, 0, sizeof g);

@@ -11,7 +11,8 @@
 // RESULT (profiles/r01_attention_decomposition.txt): correct, and the issue chain is gone — with the exponentials
 // disabled v7 runs in 0.49 ms where v4 needs 0.63 ms — but with them the softmax warps are now the bottleneck at the same
 // ~1560 cycles per block (two CTAs' exponential passes saturate the SM's MUFU pipe, ~80 % of its mixed-instruction rate),
-// so the full kernel is only 1 % faster than v4.  Kept as ESMB200_ATTN=7; v4 stays the default.
+// so the full kernel is only 1 % faster than v4; moving a quarter of the exponentials to the FMA pipe (exp2_fma below)
+// brings it to 0.594 ms (578 TFLOP/s, +4.7 % over v4).  This is the default kernel; ESMB200_ATTN=4 selects v4.
 // To keep the hand-offs to one barrier per direction, P_g is stored over the first 32 columns of its own S_g buffer
 // (every softmax thread has read its whole S row into registers before it writes P), so
 //   * Q.K^T(g+3), which overwrites S buffer g%3, is gated by pv_done(g) alone — that also implies S_g was read;
@@ -30,6 +31,26 @@
 #include "common.cuh"
 
 namespace esmb200 {
+
+// 2^x on the FMA pipe (Cody-Waite range reduction + cubic minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5,
+// well below the fp16 rounding of P): used for one pair of keys in ESMB200_ATTN_POLY to take load off the MUFU pipe,
+// which bounds this kernel (16 ex2/clk/SM).  x <= ~12 here; very negative x is clamped to 2^-126 (rounds to 0 in fp16).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float r = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of r hold round(x)
+  const float f = x - (r - 12582912.0f);    // in [-0.5, 0.5]
+  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
+// Every ESMB200_ATTN_POLY-th pair of keys takes the FMA-pipe exponential (0 = none).  Measured at B=64 (ms per launch):
+// 0: 0.615, 4 (25 %): 0.594, 3 (37.5 %): 0.651, 2 (50 %): 0.658 — beyond a quarter the extra ALU/FMA instructions cost more
+// than the MUFU cycles they save.
+#ifndef ESMB200_ATTN_POLY
+#define ESMB200_ATTN_POLY 4
+#endif
 
 namespace attn7_cfg {
 using namespace attn4_cfg;
@@ -247,8 +268,9 @@ attention_fwd_kernel_v7(const __grid_constant__ CUtensorMap tmap_q, const __grid
                 const float p0 = fmaf(s0, LOG2E, mneg);
                 const float p1 = fmaf(s1, LOG2E, mneg);
 #else
-                const float p0 = ex2_approx(fmaf(s0, LOG2E, mneg));
-                const float p1 = ex2_approx(fmaf(s1, LOG2E, mneg));
+                const bool on_fma = ESMB200_ATTN_POLY > 0 && (i % (ESMB200_ATTN_POLY > 0 ? ESMB200_ATTN_POLY : 1)) == 0;
+                const float p0 = on_fma ? exp2_fma(fmaf(s0, LOG2E, mneg)) : ex2_approx(fmaf(s0, LOG2E, mneg));
+                const float p1 = on_fma ? exp2_fma(fmaf(s1, LOG2E, mneg)) : ex2_approx(fmaf(s1, LOG2E, mneg));
 #endif
                 sum[i & 3] += p0 + p1;
                 pk[c][i] = pack_half2(p0, p1);
