@@ -730,6 +730,8 @@ size_t esmb200_axial_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t R,
   return esmb200_workspace_bytes(E, F, B * C, R) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
 }
 
+// (A CUDA-graph replay of this launch sequence was measured: 20.70 vs 20.77 ms per 128 x 512 MSA — the ~2 ms between the
+// sum of the kernel times and the wall time are not host launch overhead, so the calls stay plain stream launches.)
 int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer* const* col_layers, int32_t n_layers,
                                 float* x, const uint8_t* pad_mask, const uint8_t* col_pad_mask, int32_t B, int32_t R,
                                 int32_t C, float* const* row_attn_out, void* workspace, size_t workspace_bytes,
@@ -836,6 +838,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
   }
   return ESMB200_OK;
 }
+
 
 
 int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const float* pos_table, const float* msa_pos,
