@@ -42,7 +42,7 @@ constexpr int S_A_BYTES = S_BM * 128, S_B_BYTES = S_BN * 128;
 constexpr int S_STAGE_BYTES = S_A_BYTES + S_B_BYTES;                 // 48 KB
 constexpr int S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + 1024 + 256;
 // update
-constexpr int V_BM = 128, V_ROWS = 4, V_STAGES = 3;
+constexpr int V_BM = 128, V_ROWS = 4, V_STAGES = 2;  // 2 stages = 96 KB: two CTAs per SM, one's epilogue under the other's MMAs
 constexpr int V_P_BYTES = V_BM * 128, V_V_BYTES = 64 * 128;          // 16 KB + 4 x 8 KB
 constexpr int V_STAGE_BYTES = V_P_BYTES + V_ROWS * V_V_BYTES;        // 48 KB
 constexpr int V_SMEM_BYTES = V_STAGES * V_STAGE_BYTES + 1024 + 256;
@@ -205,7 +205,7 @@ tied_softmax_kernel(const TiedParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // ctx_r = P V_r for 4 alignment rows r per CTA
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(tied_cfg::NUM_THREADS, 1)
+__global__ void __launch_bounds__(tied_cfg::NUM_THREADS, 2)
 tied_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_v,
                const TiedParams p) {
   using namespace tied_cfg;
