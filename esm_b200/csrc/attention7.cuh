@@ -12,7 +12,7 @@
 // disabled v7 runs in 0.49 ms where v4 needs 0.63 ms — but with them the softmax warps are now the bottleneck at the same
 // ~1560 cycles per block (two CTAs' exponential passes saturate the SM's MUFU pipe, ~80 % of its mixed-instruction rate),
 // so the full kernel is only 1 % faster than v4; moving a quarter of the exponentials to the FMA pipe (exp2_fma below)
-// brings it to 0.594 ms (578 TFLOP/s, +4.7 % over v4).  This is the default kernel; ESMB200_ATTN=4 selects v4.
+// and packed FFMA2/FADD2 arithmetic bring it to 0.577 ms (595 TFLOP/s, +8 % over v4).  This is the default kernel; ESMB200_ATTN=4 selects v4.
 // To keep the hand-offs to one barrier per direction, P_g is stored over the first 32 columns of its own S_g buffer
 // (every softmax thread has read its whole S row into registers before it writes P), so
 //   * Q.K^T(g+3), which overwrites S buffer g%3, is gated by pv_done(g) alone — that also implies S_g was read;
@@ -45,9 +45,25 @@ __device__ __forceinline__ float exp2_fma(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
-// Every ESMB200_ATTN_POLY-th pair of keys takes the FMA-pipe exponential (0 = none).  Measured at B=64 (ms per launch):
-// 0: 0.615, 4 (25 %): 0.594, 3 (37.5 %): 0.651, 2 (50 %): 0.658 — beyond a quarter the extra ALU/FMA instructions cost more
-// than the MUFU cycles they save.
+// Every ESMB200_ATTN_POLY-th pair of keys takes the FMA-pipe exponential (0 = none).  Measured at B=64 (ms per launch),
+// scalar arithmetic: 0: 0.615, 4 (25 %): 0.594, 3 (37.5 %): 0.651, 2 (50 %): 0.658; with the packed FFMA2/FADD2 forms used
+// now: 0: 0.621, 4: 0.577, 3: 0.593, 2: 0.618 — beyond a quarter the extra ALU/FMA instructions cost more than the MUFU
+// cycles they save (the SM's issue slots are ~60 % busy in this kernel, profiles/r01_ncu_attention_v7_and_tied.txt).
+// the same for two values at once with packed FFMA2 / FADD2 arithmetic
+__device__ __forceinline__ void exp2_fma_pair(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float r0, r1, n0, n1, f0, f1;
+  add2(r0, r1, x0, x1, 12582912.0f, 12582912.0f);
+  add2(n0, n1, r0, r1, -12582912.0f, -12582912.0f);
+  fma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);
+  fma2(p0, p1, f0, f1, 0.0551716685f, 0.0551716685f, 0.2426111251f, 0.2426111251f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.6932609677f, 0.6932609677f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.9999280572f, 0.9999280572f);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
 #ifndef ESMB200_ATTN_POLY
 #define ESMB200_ATTN_POLY 4
 #endif
@@ -264,15 +280,20 @@ attention_fwd_kernel_v7(const __grid_constant__ CUtensorMap tmap_q, const __grid
               for (int i = 0; i < 16; ++i) {
                 const float s0 = __uint_as_float(sv[c][2 * i]), s1 = __uint_as_float(sv[c][2 * i + 1]);
                 mx[i & 3] = fmaxf(mx[i & 3], fmaxf(s0, s1));
+                float x0, x1, p0, p1;
+                fma2(x0, x1, s0, s1, LOG2E, LOG2E, mneg, mneg);  // FFMA2: both keys of the pair in one instruction
 #ifdef ESMB200_ATTN_X_NOEXP  // experiment: no MUFU work
-                const float p0 = fmaf(s0, LOG2E, mneg);
-                const float p1 = fmaf(s1, LOG2E, mneg);
+                p0 = x0;
+                p1 = x1;
 #else
-                const bool on_fma = ESMB200_ATTN_POLY > 0 && (i % (ESMB200_ATTN_POLY > 0 ? ESMB200_ATTN_POLY : 1)) == 0;
-                const float p0 = on_fma ? exp2_fma(fmaf(s0, LOG2E, mneg)) : ex2_approx(fmaf(s0, LOG2E, mneg));
-                const float p1 = on_fma ? exp2_fma(fmaf(s1, LOG2E, mneg)) : ex2_approx(fmaf(s1, LOG2E, mneg));
+                if (ESMB200_ATTN_POLY > 0 && (i % (ESMB200_ATTN_POLY > 0 ? ESMB200_ATTN_POLY : 1)) == 0) {
+                  exp2_fma_pair(x0, x1, p0, p1);
+                } else {
+                  p0 = ex2_approx(x0);
+                  p1 = ex2_approx(x1);
+                }
 #endif
-                sum[i & 3] += p0 + p1;
+                add2(sum[(i & 1) * 2], sum[(i & 1) * 2 + 1], sum[(i & 1) * 2], sum[(i & 1) * 2 + 1], p0, p1);  // FADD2
                 pk[c][i] = pack_half2(p0, p1);
               }
             } else {

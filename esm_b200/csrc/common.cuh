@@ -431,6 +431,24 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 // 2^x, MUFU.EX2 (max rel. error 2^-22; ex2(-inf) = +0)
+// packed fp32 pair arithmetic (FFMA2 / FADD2 on sm_100): one instruction for two lanes of data
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
