@@ -36,6 +36,7 @@ EXPORTS = (
     "esmb200_axial_workspace_bytes",
     "esmb200_axial_stack_forward",
     "esmb200_msa_embed",
+    "esmb200_contact_accumulate",
     "esmb200_layernorm_f16",
     "esmb200_convert_f16",
     "esmb200_launch_count",
@@ -135,6 +136,9 @@ def _declare(lib):
     lib.esmb200_msa_embed.restype = c_int32
     lib.esmb200_msa_embed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float,
                                       c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.esmb200_contact_accumulate.restype = c_int32
+    lib.esmb200_contact_accumulate.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                               c_int32, c_int32, c_int32, c_void_p]
     lib.esmb200_launch_count.restype = ctypes.c_longlong
     lib.esmb200_launch_count.argtypes = []
     lib.esmb200_profile_enable.restype = c_int32

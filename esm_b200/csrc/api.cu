@@ -866,6 +866,25 @@ int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const flo
 }
 
 
+int esmb200_contact_accumulate(const float* attn, int64_t batch_stride, const float* w, const uint8_t* keep, float* acc,
+                               float* a1, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi, void* stream) {
+  if (!attn || !w || !acc || !a1) return fail(ESMB200_EINVAL, "null argument");
+  const int S = hi - lo;
+  if (B <= 0 || H <= 0 || T <= 0 || lo < 0 || hi > T || S <= 0 || B > 65535) return fail(ESMB200_EINVAL, "bad shape");
+  if (S > 1024) return fail(ESMB200_EINVAL, "contact head supports at most 1024 positions");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(T_PROBS, st);
+  const size_t smem = (size_t)8 * S * sizeof(float);
+  dim3 grid((S + 15) / 16, B);  // 8 warps x 2 rows
+  if (S <= 512)
+    contact_accumulate_kernel<2, 16, 2><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, a1, H, T, lo, S);
+  else
+    contact_accumulate_kernel<2, 32, 1><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, a1, H, T, lo, S);
+  CK(cudaGetLastError());
+  return ESMB200_OK;
+}
+
+
 int esmb200_mean_pool(const float* x, const int32_t* lengths, float* out, int32_t B, int32_t T, int32_t E,
                       void* stream) {
   if (!x || !lengths || !out) return fail(ESMB200_EINVAL, "null argument");

@@ -264,4 +264,104 @@ msa_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ e
   }
 }
 
+// Contact head, per-layer accumulation (/root/reference/esm/modules.py:338-357 with symmetrize :27-29 and apc :32-41,
+// restated so that the [B, L*H, S, S] temporaries are never formed): with A_c the eos-masked, bos/eos-cropped attention
+// map of channel c = (layer, head),
+//     logit_ij = sum_c w_c (A_c + A_c^T)_ij - sum_c (w_c / a12_c) a1_c[i] a1_c[j] + b,
+//     a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum_i a1_c[i].
+// This kernel reads one layer's maps [B,H,T,T] ONCE and produces  acc[b,i,j] += sum_h w_h A_h[i,j]  and
+// a1[b,h,i] += rowsum + colsum  (a1 zeroed by the caller).  CTA = (16 query rows, batch element b), 8 warps, two CTAs per SM when S <= 512; a warp owns
+// RPW rows, a lane owns the columns lane + 32 k: row sums by warp shuffles, column sums through an [8][S] shared-memory
+// stage and one global atomic per (head, column) and CTA, acc in registers across the head loop (plain read-modify-write:
+// every acc row belongs to exactly one CTA and layers are separate launches).
+template <int RPW, int MAXC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+contact_accumulate_kernel(const float* __restrict__ attn, long long batch_stride, const float* __restrict__ w,
+                          const uint8_t* __restrict__ keep, float* __restrict__ acc, float* __restrict__ a1, int H,
+                          int T, int lo, int S) {
+  extern __shared__ float s_col[];  // [8][S]
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int i0 = blockIdx.x * (8 * RPW) + warp * RPW;
+  const uint8_t* kp = keep ? keep + (size_t)b * T : nullptr;
+  float ac[RPW][MAXC];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) ac[r][c] = 0.f;
+  float kj[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = lane + 32 * c;
+    kj[c] = (j < S && (!kp || kp[lo + j])) ? 1.f : 0.f;
+  }
+  float ki[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) ki[r] = (i0 + r < S && (!kp || kp[lo + i0 + r])) ? 1.f : 0.f;
+
+  // software pipeline over the heads: the RPW x MAXC loads of head h+1 are in flight while head h is reduced
+  float v[RPW][MAXC];
+  auto load_head = [&](int h) {
+    const float* base = attn + (size_t)b * batch_stride + (size_t)h * T * T + (size_t)lo * T + lo;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const float* row = base + (size_t)(i0 + r) * T;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int j = lane + 32 * c;
+        v[r][c] = (ki[r] != 0.f && j < S) ? __ldg(row + j) : 0.f;
+      }
+    }
+  };
+  load_head(0);
+  for (int h = 0; h < H; ++h) {
+    const float wh = __ldg(w + h);
+    float colp[MAXC];
+    float rs[RPW];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) colp[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      rs[r] = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const float x = v[r][c] * kj[c];
+        ac[r][c] = fmaf(wh, x, ac[r][c]);
+        colp[c] += x;
+        rs[r] += x;
+      }
+    }
+    if (h + 1 < H) load_head(h + 1);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const float t = warp_sum(rs[r]);
+      if (lane == 0 && ki[r] != 0.f) atomicAdd(a1 + ((size_t)b * H + h) * S + i0 + r, t);
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int j = lane + 32 * c;
+      if (j < S) s_col[warp * S + j] = colp[c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < S; j += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += s_col[q * S + j];
+      if (t != 0.f) atomicAdd(a1 + ((size_t)b * H + h) * S + j, t);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    if (i0 + r < S) {
+      float* dst = acc + ((size_t)b * S + i0 + r) * S;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int j = lane + 32 * c;
+        if (j < S) dst[j] += ac[r][c];
+      }
+    }
+  }
+}
+
 }  // namespace esmb200

@@ -285,13 +285,41 @@ class ContactPredictionHead(nn.Module):
         """modules.py:338-357 evaluated without the [B, L*H, S, S] temporaries of symmetrize/apc (which need ~6x the
         24 GB attention stack of configs[3]): with A_c the eos-masked, cropped map of channel c = (layer, head),
             logit_ij = sum_c w_c (A_c + A_c^T)_ij - sum_c (w_c / a12_c) a1_c[i] a1_c[j] + b,
-            a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum(a1_c),
-        accumulated layer by layer: a weighted sum over heads and a rank-H outer product per layer."""
+            a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum(a1_c).
+        On the GPU every layer's maps are read once by esmb200_contact_accumulate (sum over heads + row/column sums);
+        the rank-(L*H) correction, the symmetrisation and the sigmoid act on [B,S,S] / [B,L*H,S] tensors."""
         B, L, H, T, _ = attentions.shape
         lo = 1 if self.prepend_bos else 0
         hi = T - 1 if self.append_eos else T
         S = hi - lo
         w = self.regression.weight.view(L, H).to(attentions.dtype)
+        if not (attentions.is_cuda and attentions.dtype == torch.float32 and attentions.is_contiguous()):
+            return self._forward_torch(tokens, attentions, w, lo, hi)
+        lib = _lib.load()
+        dev = attentions.device
+        keep8 = tokens.ne(self.eos_idx).to(torch.uint8).contiguous() if self.append_eos else None
+        acc = torch.zeros((B, S, S), dtype=torch.float32, device=dev)
+        a1 = torch.zeros((L, B, H, S), dtype=torch.float32, device=dev)   # layer-major: one [B,H,S] block per launch
+        wl = w.float().contiguous()
+        with torch.cuda.device(dev):
+            for l in range(L):
+                _lib.check(lib.esmb200_contact_accumulate(
+                    ctypes.c_void_p(attentions.data_ptr() + l * H * T * T * 4), L * H * T * T,
+                    ctypes.c_void_p(wl.data_ptr() + l * H * 4), _ptr(keep8), _ptr(acc),
+                    ctypes.c_void_p(a1.data_ptr() + l * B * H * S * 4), B, H, T, lo, hi, _stream()))
+        a1f = a1.permute(1, 0, 2, 3).reshape(B, L * H, S)
+        a12 = a1f.sum(-1, keepdim=True)                                   # [B, L*H, 1]
+        coef = w.reshape(1, L * H, 1) / a12
+        corr = torch.einsum("bci,bcj->bij", a1f * coef, a1f)
+        logits = acc + acc.transpose(-1, -2) - corr
+        if self.regression.bias is not None:
+            logits = logits + self.regression.bias
+        return self.activation(logits)
+
+    def _forward_torch(self, tokens, attentions, w, lo, hi):
+        """The same formula with PyTorch ops (non-CUDA or non-fp32 inputs; cross-check in the tests)."""
+        B, L, H, T, _ = attentions.shape
+        S = hi - lo
         keep = None
         if self.append_eos:
             keep = tokens.ne(self.eos_idx).to(attentions)[:, lo:hi]  # [B,S]

@@ -176,6 +176,15 @@ int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const flo
                       int32_t msa_pos_dim, const float* ln_weight, const float* ln_bias, float eps, float* x,
                       int32_t B, int32_t R, int32_t C, int32_t E, int32_t padding_idx, void* stream);
 
+/* Contact head, one layer's share (ContactPredictionHead.forward esm/modules.py:338-357, symmetrize :27-29, apc :32-41):
+ * attn = that layer's attention maps fp32 [B,H,T,T] (batch_stride floats between batch elements, so a slice of a stacked
+ * [B,L,H,T,T] tensor works), cropped to positions [lo,hi) and multiplied by keep[b,i]*keep[b,j] (keep [B,T], 1 = not
+ * <eos>; NULL = no masking). Adds sum_h w[h]*A_h to acc [B,S,S] and rowsum(A_h)+colsum(A_h) to a1 [B,H,S] (S = hi-lo;
+ * the caller zeroes both before the first layer); the caller finishes with
+ * sigmoid(acc + acc^T - sum_c (w_c/sum_i a1_c[i]) a1_c a1_c^T + bias). */
+int esmb200_contact_accumulate(const float* attn, int64_t batch_stride, const float* w, const uint8_t* keep, float* acc,
+                               float* a1, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi, void* stream);
+
 /* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,
                           float eps, void* stream);

@@ -42,6 +42,15 @@ def main():
             res[name]["finite"] = bool(torch.isfinite(out["contacts"]).all())
         del out
         torch.cuda.empty_cache()
+    if os.environ.get("C4_PROFILE"):
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            out = model(tok, repr_layers=[36], return_contacts=True)
+            torch.cuda.synchronize()
+        tab = prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "config4_profile.txt"), "w").write(tab)
+        del out
     res["config"] = {"model": "esm2_t36_3B_UR50D (random init)", "B": B, "T": T}
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -180,3 +180,33 @@ def test_extract_cli_writes_reference_schema(tmp_path):
         assert rel_fro(r["mean_representations"][L], want.mean(0)) <= REL_FRO
         assert r["contacts"].shape == (len(seq), len(seq))
         assert float((r["contacts"] - ref["contacts"][0]).abs().max()) <= CONTACT_ABS
+
+
+@pytest.mark.parametrize("T,eos", [(40, True), (130, True), (600, True), (77, False)])
+def test_contact_head_native_accumulation_matches_torch_formula(T, eos):
+    """esmb200_contact_accumulate (one pass over each layer's maps) + the small [B,S,S] tail against the same formula
+    evaluated with PyTorch ops on the same CUDA tensors; both row-tile variants (S <= 512 / <= 1024), eos masking with
+    padded sequences, and the MSA case (no eos appended)."""
+    from esm_b200.model import ContactPredictionHead
+    torch.manual_seed(T)
+    B, L, H = 3, 2, 5
+    head = ContactPredictionHead(L * H, True, eos, eos_idx=2).cuda()
+    with torch.no_grad():
+        head.regression.weight.normal_(0, 1.5)
+        head.regression.bias.fill_(0.3)
+    tok = torch.randint(4, 24, (B, T))
+    tok[:, 0] = 0
+    if eos:
+        tok[0, -1] = 2
+        tok[1, T - 7] = 2
+        tok[1, T - 6:] = 1
+        tok[2, T // 2] = 2
+        tok[2, T // 2 + 1:] = 1
+    att = torch.rand(B, L, H, T, T).softmax(-1).cuda()
+    tok = tok.cuda()
+    with torch.no_grad():
+        got = head(tok, att)
+        lo, hi = 1, (T - 1 if eos else T)
+        ref = head._forward_torch(tok, att, head.regression.weight.view(L, H), lo, hi)
+    assert got.shape == (B, hi - lo, hi - lo)
+    assert float((got - ref).abs().max()) <= 2e-5

@@ -69,9 +69,10 @@ def test_padded_msas_against_reference_golden(golden_dir):
             assert float((col - fx["col_attn_sample"]).abs()[:, qkeep].max()) <= 1e-2
 
 
-@pytest.mark.parametrize("B,R,C", [(1, 10, 77), (2, 5, 130), (1, 3, 300)])
+@pytest.mark.parametrize("B,R,C", [(1, 10, 77), (2, 5, 130), (1, 3, 300), (1, 130, 40)])
 def test_axial_layer_ragged_shapes_against_oracle(B, R, C):
-    """Row counts that are not a multiple of the 4-row update tile, column counts that are not multiples of 64 / 4."""
+    """Row counts that are not a multiple of the 4-row update tile (and > 128: two query tiles in the column attention),
+    column counts that are not multiples of 64 / 4."""
     from oracle import msa_oracle
     layer, sd = build(128, 512, 2)
     g = torch.Generator().manual_seed(9)
