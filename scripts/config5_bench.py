@@ -40,10 +40,12 @@ def main():
            "msa_per_s": round(1e3 / ms, 2), "TFLOP/s": round(flops / ms / 1e9, 1), "finite": bool(torch.isfinite(y).all())}
     # the whole model (embedding prologue, 12 layers, final LayerNorm, LM head) on tokens (1, 128, 512)
     from esm_b200 import pretrained
-    from oracle.msa_oracle import make_msa_tokens
     model, _ = pretrained.esm_msa1b_t12_100M_UR50S()
     model = model.cuda()
-    tokens = make_msa_tokens(1, R, C, seed=1234).cuda()
+    gt = torch.Generator().manual_seed(1234)
+    tokens = torch.randint(4, 24, (1, R, C), generator=gt)   # the 20 standard amino acids, <cls> in column 0, no padding
+    tokens[:, :, 0] = 0
+    tokens = tokens.cuda()
     for _ in range(2):
         out = model(tokens, repr_layers=[12])
     torch.cuda.synchronize()
