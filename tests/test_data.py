@@ -24,3 +24,35 @@ def test_batches_respect_budget_and_cover_everything():
     assert seen == list(range(200))
     for b in batches:
         assert (max(len(seqs[i]) for i in b) + 1) * len(b) <= 1024 or len(b) == 1
+
+
+def test_extract_file_writer_and_staging_plan(tmp_path):
+    """Host-side pieces of the extraction driver: the background writer saves every queued object and reports the
+    count; the staging plan covers 256-byte aligned carving."""
+    import torch
+    from esm_b200.extract_cli import FileWriter, plan_bytes
+    w = FileWriter(n_threads=3, depth=4)
+    for i in range(25):
+        w.put(tmp_path / f"s{i}.pt", {"label": f"s{i}", "x": torch.full((3,), float(i))})
+    assert w.close() == 25
+    for i in (0, 7, 24):
+        r = torch.load(tmp_path / f"s{i}.pt", weights_only=False)
+        assert r["label"] == f"s{i}" and float(r["x"][0]) == float(i)
+    shapes = [((3, 5, 7), 4), ((3, 7), 4), ((3, 3, 3), 4)]
+    need = 0
+    for shape, es in shapes:          # what StagingSlot.take() does
+        n = es
+        for s in shape:
+            n *= s
+        need = (need + 255) // 256 * 256 + n
+    assert plan_bytes(shapes) >= need
+
+
+def test_extract_file_writer_surfaces_errors(tmp_path):
+    import pytest
+    import torch
+    from esm_b200.extract_cli import FileWriter
+    w = FileWriter(n_threads=1)
+    w.put(tmp_path / "no_such_dir" / "x.pt", {"x": torch.zeros(1)})
+    with pytest.raises(Exception):
+        w.close()
