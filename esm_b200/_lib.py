@@ -42,6 +42,7 @@ EXPORTS = (
     "esmb200_launch_count",
     "esmb200_profile_enable",
     "esmb200_profile_read",
+    "esmb200_set_option",
 )
 
 EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU, EPI_BIAS_F32, EPI_BIAS_GELU_F32 = range(5)
@@ -145,6 +146,8 @@ def _declare(lib):
     lib.esmb200_profile_enable.argtypes = [c_int32]
     lib.esmb200_profile_read.restype = c_int32
     lib.esmb200_profile_read.argtypes = [POINTER(c_int32), POINTER(c_float), c_int32]
+    lib.esmb200_set_option.restype = c_int32
+    lib.esmb200_set_option.argtypes = [c_char_p, c_int32]
     lib.esmb200_convert_f16.restype = c_int32
     lib.esmb200_convert_f16.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
 

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libesmb200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "gemm2.cuh", "attention.cuh", "attention2.cuh", "attention3.cuh", "attention4.cuh", "attention5.cuh", "attention7.cuh", "tied_attention.cuh", "elementwise.cuh", os.path.join("..", "..", "include", "esmb200.h")]
+HEADERS = ["common.cuh", "gemm_common.cuh", "gemm2.cuh", "attention_common.cuh", "attention_probs.cuh", "attention7.cuh",
+           "attention8.cuh", "tied_attention.cuh", "elementwise.cuh", os.path.join("..", "..", "include", "esmb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -30,20 +31,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """Build libesmb200.so.  `defines` / `out` produce developer variants (e.g. -DESMB200_EXPERIMENTS for the
+    profiling-only GEMM epilogues) that are loaded through ESMB200_LIB_PATH; the product library takes neither."""
+    if not force and out == OUT and not _stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libesmb200.so must be built with the CUDA 12.9 toolkit (sm_100a)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", out] + SOURCES)
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv or bool(defs), verbose="-v" in sys.argv, defines=defs,
+                out=os.path.abspath(outs[0]) if outs else OUT))

@@ -16,17 +16,15 @@
 #include <string>
 #include <vector>
 
-#include "attention.cuh"
-#include "attention2.cuh"
-#include "attention3.cuh"
-#include "attention4.cuh"
-#include "attention5.cuh"
+#include <mutex>
+
 #include "attention7.cuh"
-#include "tied_attention.cuh"
+#include "attention8.cuh"
+#include "attention_probs.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
-#include "gemm.cuh"
 #include "gemm2.cuh"
+#include "tied_attention.cuh"
 
 using namespace esmb200;
 
@@ -55,7 +53,8 @@ int fail_cuda(cudaError_t e, const char* what) {
 // ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) --------------------
 enum ProfTag : int { T_LN1 = 0, T_QKV, T_ATTN, T_OUT, T_LN2, T_FC1, T_FC2, T_KEYBITS, T_EMBED, T_LN_F32, T_PROBS,
                      T_CONVERT, T_GEMM_OTHER, T_MEANPOOL, T_TIED_SCORES, T_TIED_SOFTMAX, T_TIED_PV, T_COUNT };
-struct Profiler {
+struct Profiler {  // process-wide, guarded by `mu`: launches may come from several host threads / streams
+  std::mutex mu;
   bool on = false;
   std::vector<cudaEvent_t> ev;  // pairs (start, stop)
   std::vector<int> tag;
@@ -67,19 +66,20 @@ Profiler g_prof;
 struct ProfScope {
   cudaStream_t st;
   bool rec;
+  size_t slot = 0;
   ProfScope(int tag, cudaStream_t s) : st(s), rec(false) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
     ++g_prof.launches;
     if (g_prof.on && g_prof.used + 2 <= g_prof.ev.size()) {
       rec = true;
+      slot = g_prof.used;
+      g_prof.used += 2;
       g_prof.tag.push_back(tag);
-      cudaEventRecord(g_prof.ev[g_prof.used], st);
+      cudaEventRecord(g_prof.ev[slot], st);
     }
   }
   ~ProfScope() {
-    if (rec) {
-      cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
-      g_prof.used += 2;
-    }
+    if (rec) cudaEventRecord(g_prof.ev[slot + 1], st);
   }
 };
 
@@ -129,88 +129,85 @@ int make_tmap_f16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t col
   return make_tmap_2d(map, ptr, 2, rows, cols, ld_elems, box_rows);
 }
 
-// GEMM implementation: 2 = CTA-pair kernel (gemm2.cuh, default), 1 = single-CTA kernel (gemm.cuh).
-int gemm_version() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("ESMB200_GEMM");
-    v = (e && e[0] == '1') ? 1 : 2;
-  }
-  return v;
-}
+// attention implementation: 8 = attention8.cuh (4 CTAs/SM, default), 7 = attention7.cuh (2 CTAs/SM, two MMA issuing
+// threads; kept for A/B runs).  ESMB200_ATTN_POLY = n sends every n-th pair of exponentials of v8 to the FMA pipe.
+int g_attn_version = -1, g_attn_poly = -1;  // -1: take the environment / default on first use
 
-// attention implementation: 7 = attention7.cuh (persistent, two MMA issuing threads, default); 4 = attention4.cuh
-// (persistent, one issuing thread); 5 = 4 + TMEM lookahead (measured slower); 3 / 2 / 1 = earlier kernels (A/B runs)
 int attn_version() {
-  static int v = 0;
-  if (v == 0) {
+  if (g_attn_version < 0) {
     const char* e = getenv("ESMB200_ATTN");
-    v = (e && e[0] >= '1' && e[0] <= '7' && e[0] != '6') ? (e[0] - '0') : 7;
+    g_attn_version = (e && e[0] == '7') ? 7 : 8;
   }
-  return v;
+  return g_attn_version;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+int attn_poly() {
+  if (g_attn_poly < 0) {
+    const char* e = getenv("ESMB200_ATTN_POLY");
+    g_attn_poly = (e && (e[0] == '0' || e[0] == '2' || e[0] == '3' || e[0] == '4')) ? (e[0] - '0') : 3;
   }
-  return n;
+  return g_attn_poly;
+}
+
+cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& ap, int sms,
+                                 cudaStream_t st) {
+  if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
+  switch (attn_poly()) {
+    case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
+    case 2: return launch_attention_v8_poly<2>(tq, tkv, ap, sms, st);
+    case 4: return launch_attention_v8_poly<4>(tq, tkv, ap, sms, st);
+    default: return launch_attention_v8_poly<3>(tq, tkv, ap, sms, st);
+  }
+}
+
+constexpr int kMaxDevices = 64;
+
+int num_sms() {  // per device: one process may drive several GPUs
+  static int n[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 int check_device() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return fail(ESMB200_ECUDA, "no CUDA device");
+  static int ok[kMaxDevices] = {};  // 0 unknown, 1 sm_100, -1 other
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(ESMB200_ECUDA, "no CUDA device");
+  if (dev < 0 || dev >= kMaxDevices) return fail(ESMB200_ECUDA, "device ordinal out of range");
+  if (ok[dev] == 0) {
+    int major = 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    ok = (major == 10) ? 1 : 0;
+    ok[dev] = (major == 10) ? 1 : -1;
   }
-  if (!ok) return fail(ESMB200_ECUDA, "esmb200 requires an sm_100a (Blackwell B200) device; there is no fallback path");
+  if (ok[dev] < 0)
+    return fail(ESMB200_ECUDA, "esmb200 requires an sm_100a (Blackwell B200) device; there is no fallback path");
   return ESMB200_OK;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const GemmParams& p,
+int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                 cudaStream_t st, int tag = T_GEMM_OTHER) {
   ProfScope ps(tag, st);
   cudaError_t e;
-  if (tout != nullptr) {
-    static const bool direct = [] { const char* e = getenv("ESMB200_EPI_DIRECT"); return e && e[0] == '1'; }();
-    if (direct && (epi == EPI_QKV_ROPE || epi == EPI_BIAS_GELU)) {
-      e = epi == EPI_QKV_ROPE ? launch_gemm2_epi<EPI_QKV_ROPE, true>(ta, tb, *tout, p, num_sms(), st)
-                              : launch_gemm2_epi<EPI_BIAS_GELU, true>(ta, tb, *tout, p, num_sms(), st);
-      if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");
-      return ESMB200_OK;
-    }
-    switch (epi) {
-      case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_BIAS_GELU: e = launch_gemm2_epi<EPI_BIAS_GELU>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_BIAS_F32: e = launch_gemm2_epi<EPI_BIAS_F32>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_BIAS_GELU_F32: e = launch_gemm2_epi<EPI_BIAS_GELU_F32>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_NONE: e = launch_gemm2_epi<EPI_NONE>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_LDONLY: e = launch_gemm2_epi<EPI_LDONLY>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_LD_X16: e = launch_gemm2_epi<EPI_LD_X16>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_LD_4WARPS: e = launch_gemm2_epi<EPI_LD_4WARPS>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_LD_BATCH: e = launch_gemm2_epi<EPI_LD_BATCH>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_GELU_MATHONLY: e = launch_gemm2_epi<EPI_GELU_MATHONLY>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_F16_STOREONLY: e = launch_gemm2_epi<EPI_F16_STOREONLY>(ta, tb, *tout, p, num_sms(), st); break;
-      case EPI_FMA_MATHONLY: e = launch_gemm2_epi<EPI_FMA_MATHONLY>(ta, tb, *tout, p, num_sms(), st); break;
-      default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
-    }
-    if (e != cudaSuccess) return fail_cuda(e, "gemm2 launch");
-    return ESMB200_OK;
-  }
   switch (epi) {
-    case EPI_QKV_ROPE: e = launch_gemm_epi<EPI_QKV_ROPE>(ta, tb, p, num_sms(), st); break;
-    case EPI_BIAS_RESIDUAL: e = launch_gemm_epi<EPI_BIAS_RESIDUAL>(ta, tb, p, num_sms(), st); break;
-    case EPI_BIAS_GELU: e = launch_gemm_epi<EPI_BIAS_GELU>(ta, tb, p, num_sms(), st); break;
-    case EPI_BIAS_F32: e = launch_gemm_epi<EPI_BIAS_F32>(ta, tb, p, num_sms(), st); break;
-    case EPI_BIAS_GELU_F32: e = launch_gemm_epi<EPI_BIAS_GELU_F32>(ta, tb, p, num_sms(), st); break;
+    case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_BIAS_GELU: e = launch_gemm2_epi<EPI_BIAS_GELU>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_BIAS_F32: e = launch_gemm2_epi<EPI_BIAS_F32>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_BIAS_GELU_F32: e = launch_gemm2_epi<EPI_BIAS_GELU_F32>(ta, tb, tout, p, num_sms(), st); break;
+#ifdef ESMB200_EXPERIMENTS  // profiling-only epilogues (profiles/r01_epilogue_experiments.txt)
+    case EPI_NONE: e = launch_gemm2_epi<EPI_NONE>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_LDONLY: e = launch_gemm2_epi<EPI_LDONLY>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_LD_X16: e = launch_gemm2_epi<EPI_LD_X16>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_LD_4WARPS: e = launch_gemm2_epi<EPI_LD_4WARPS>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_LD_BATCH: e = launch_gemm2_epi<EPI_LD_BATCH>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_GELU_MATHONLY: e = launch_gemm2_epi<EPI_GELU_MATHONLY>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_F16_STOREONLY: e = launch_gemm2_epi<EPI_F16_STOREONLY>(ta, tb, tout, p, num_sms(), st); break;
+    case EPI_FMA_MATHONLY: e = launch_gemm2_epi<EPI_FMA_MATHONLY>(ta, tb, tout, p, num_sms(), st); break;
+#endif
     default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
   }
   if (e != cudaSuccess) return fail_cuda(e, "gemm launch");
@@ -267,18 +264,11 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
   ap.row_sum = probs ? s.row_sum : nullptr;
   cudaError_t e;
   {
+    CUtensorMap tkv;
+    rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn8_cfg::BLOCK_KV);
+    if (rc) return rc;
     ProfScope ps(T_ATTN, st);
-    if (attn_version() >= 3) {
-      CUtensorMap tkv;
-      rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn3_cfg::BLOCK_KV);
-      if (rc) return rc;
-      e = attn_version() == 7   ? launch_attention_v7(tq, tkv, ap, num_sms(), st)
-          : attn_version() == 5 ? launch_attention_v5(tq, tkv, ap, num_sms(), st)
-          : attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st)
-                                : launch_attention_v3(tq, tkv, ap, st);
-    } else {
-      e = attn_version() == 2 ? launch_attention_v2(tq, ap, st) : launch_attention(tq, ap, st);
-    }
+    e = launch_attention_fwd(tq, tkv, ap, num_sms(), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "attention launch");
   if (probs) {
@@ -314,7 +304,7 @@ struct esmb200_layer {
   __half* w_fc1;  // [F,E]
   __half* w_fc2;  // [E,F]
   float* b_qkv;   // [3E]
-  CUtensorMap tm_qkv, tm_out, tm_fc1, tm_fc2;  // B operands, box {64, 256 rows} (v1) or {64, 128 rows} (v2)
+  CUtensorMap tm_qkv, tm_out, tm_fc1, tm_fc2;  // B operands, box {64, 128 rows}
 };
 
 extern "C" {
@@ -387,7 +377,7 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
     if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + 2 * E, w->v_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) rc = fail_cuda(e, "bias pack");
   }
-  const uint32_t wbox = gemm_version() == 2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N;
+  const uint32_t wbox = gemm2_cfg::HALF_N;
   if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)E, E, E, wbox);
   if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, E, E, wbox);
   if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
@@ -442,8 +432,7 @@ int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int F, 
 
 struct ActMaps {
   CUtensorMap xn, ctx, h;       // A operands (fp16, box {64,128}); h doubles as fc1's output map
-  CUtensorMap qkv_out, x_out;   // v2 epilogue outputs: qkv fp16 [M,3E] box {64,128}; x fp32 [M,E] box {32,128}
-  bool v2;
+  CUtensorMap qkv_out, x_out;   // epilogue outputs: qkv fp16 [M,3E] box {64,128}; x fp32 [M,E] box {32,128}
 };
 
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
@@ -462,8 +451,8 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
-  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
-  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f; g.chunked = 1;
+  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
   rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st);
@@ -471,7 +460,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
   {
@@ -482,22 +471,21 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // fc1 + GELU (modules.py:138)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
-  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.v2 ? &am.h : nullptr, g, st, T_FC1);
+  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.h, g, st, T_FC1);
   if (rc) return rc;
   // fc2 + residual (modules.py:139-140)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.v2 ? &am.x_out : nullptr, g, st, T_FC2);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2);
   return rc;
 }
 
 int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int F, int M) {
-  am->v2 = gemm_version() == 2;
-  int rc = make_tmap_f16(&am->xn, ws.xn, M, E, E, gemm_cfg::BLOCK_M);
-  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, E, E, gemm_cfg::BLOCK_M);
-  if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, F, F, gemm_cfg::BLOCK_M);
-  if (!rc && am->v2) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
-  if (!rc && am->v2) rc = make_tmap_2d(&am->x_out, x, 4, M, E, E, 128);
+  int rc = make_tmap_f16(&am->xn, ws.xn, M, E, E, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, E, E, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, F, F, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
+  if (!rc) rc = make_tmap_2d(&am->x_out, x, 4, M, E, E, 128);
   return rc;
 }
 }  // namespace
@@ -585,18 +573,17 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
   if (epilogue == EPI_QKV_ROPE && (!rope_cos || !rope_sin || T <= 0 || E <= 0 || E % 64 != 0 || N != 3 * E))
     return fail(ESMB200_EINVAL, "qkv epilogue needs rope tables, T and N == 3E");
   CUtensorMap ta, tb, tout;
-  const bool v2 = gemm_version() == 2;
   const bool out_f16 = (epilogue == EPI_QKV_ROPE || epilogue == EPI_BIAS_GELU || epilogue == EPI_F16_STOREONLY ||
                         epilogue == EPI_GELU_MATHONLY || epilogue == EPI_FMA_MATHONLY);
-  rc = make_tmap_f16(&ta, a, M, K, K, gemm_cfg::BLOCK_M);
-  if (!rc) rc = make_tmap_f16(&tb, w, N, K, K, v2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N);
-  if (!rc && v2) rc = make_tmap_2d(&tout, out, out_f16 ? 2 : 4, M, N, N, 128);
+  rc = make_tmap_f16(&ta, a, M, K, K, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&tb, w, N, K, K, gemm2_cfg::HALF_N);
+  if (!rc) rc = make_tmap_2d(&tout, out, out_f16 ? 2 : 4, M, N, N, 128);
   if (rc) return rc;
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = N;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
-  return launch_gemm(epilogue, ta, tb, v2 ? &tout : nullptr, g, static_cast<cudaStream_t>(stream));
+  return launch_gemm(epilogue, ta, tb, tout, g, static_cast<cudaStream_t>(stream));
 }
 
 int esmb200_gemm_qkv_f16(const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t E, float q_scale,
@@ -608,16 +595,15 @@ int esmb200_gemm_qkv_f16(const void* a, const void* w, const float* bias, void* 
   int rc = check_device();
   if (rc) return rc;
   CUtensorMap ta, tb, tout;
-  const bool v2 = gemm_version() == 2;
-  rc = make_tmap_f16(&ta, a, M, E, E, gemm_cfg::BLOCK_M);
-  if (!rc) rc = make_tmap_f16(&tb, w, 3 * (uint64_t)E, E, E, v2 ? gemm2_cfg::HALF_N : gemm_cfg::BLOCK_N);
-  if (!rc && v2) rc = make_tmap_2d(&tout, out, 2, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
+  rc = make_tmap_f16(&ta, a, M, E, E, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&tb, w, 3 * (uint64_t)E, E, E, gemm2_cfg::HALF_N);
+  if (!rc) rc = make_tmap_2d(&tout, out, 2, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
   if (rc) return rc;
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * E; g.K = E; g.bias = bias; g.out = out; g.ldo = 3 * E;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T > 0 ? T : 1; g.E = E; g.q_scale = q_scale;
-  return launch_gemm(EPI_QKV_ROPE, ta, tb, v2 ? &tout : nullptr, g, static_cast<cudaStream_t>(stream));
+  return launch_gemm(EPI_QKV_ROPE, ta, tb, tout, g, static_cast<cudaStream_t>(stream));
 }
 
 int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,
@@ -707,8 +693,8 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
   if (rc) return rc;
   CUtensorMap tq, tkv;
   const uint64_t wide = (uint64_t)C * 3 * E;  // qkv viewed as [B*R, C*3E]: token r of column c at row r, x = c*3E
-  if ((rc = make_tmap_f16(&tq, qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_Q))) return rc;
-  if ((rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_KV))) return rc;
+  if ((rc = make_tmap_f16(&tq, qkv, (uint64_t)B * R, wide, wide, attn8_cfg::BLOCK_Q))) return rc;
+  if ((rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * R, wide, wide, attn8_cfg::BLOCK_KV))) return rc;
   AttnParams ap;
   ap.B = S; ap.T = R; ap.H = H; ap.E = E;
   ap.keybits = s.keybits; ap.kvlen = s.kvlen; ap.words = s.words;
@@ -718,8 +704,7 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
   cudaError_t e;
   {
     ProfScope ps(T_ATTN, st);
-    e = attn_version() == 4 ? launch_attention_v4(tq, tkv, ap, num_sms(), st)
-                            : launch_attention_v7(tq, tkv, ap, num_sms(), st);
+    e = launch_attention_fwd(tq, tkv, ap, num_sms(), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
   return ESMB200_OK;
@@ -765,8 +750,8 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
   if (rc) return rc;
   CUtensorMap tcq, tckv;
   const uint64_t wide = (uint64_t)C * 3 * E;
-  if ((rc = make_tmap_f16(&tcq, ws.qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_Q))) return rc;
-  if ((rc = make_tmap_f16(&tckv, ws.qkv, (uint64_t)B * R, wide, wide, attn4_cfg::BLOCK_KV))) return rc;
+  if ((rc = make_tmap_f16(&tcq, ws.qkv, (uint64_t)B * R, wide, wide, attn8_cfg::BLOCK_Q))) return rc;
+  if ((rc = make_tmap_f16(&tckv, ws.qkv, (uint64_t)B * R, wide, wide, attn8_cfg::BLOCK_KV))) return rc;
   const float row_scale = 0.125f / sqrtf((float)R);  // axial_attention.py:36-38
   cudaError_t e;
   GemmParams g;
@@ -781,7 +766,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     memset(&g, 0, sizeof g);
     g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
     g.T = 1; g.E = E; g.q_scale = row_scale;
-    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
+    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV);
     if (rc) return rc;
     if (pad_mask) {
       ProfScope ps(T_KEYBITS, st);
@@ -793,7 +778,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     if (rc) return rc;
     memset(&g, 0, sizeof g);
     g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
-    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT);
     if (rc) return rc;
     // ---------------- column attention (modules.py:208-212; axial_attention.py:182-239) ----------------
     L = col_layers[i];
@@ -805,7 +790,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     memset(&g, 0, sizeof g);
     g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
     g.T = 1; g.E = E; g.q_scale = 0.125f;
-    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.v2 ? &am.qkv_out : nullptr, g, st, T_QKV);
+    rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV);
     if (rc) return rc;
     {
       AttnParams ap;
@@ -813,13 +798,12 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
       ap.keybits = ws.as.keybits; ap.kvlen = ws.as.kvlen; ap.words = ws.as.words;
       ap.ctx = ws.ctx; ap.row_max = nullptr; ap.row_sum = nullptr; ap.cols = C;
       ProfScope ps(T_ATTN, st);
-      e = attn_version() == 4 ? launch_attention_v4(tcq, tckv, ap, num_sms(), st)
-                              : launch_attention_v7(tcq, tckv, ap, num_sms(), st);
+      e = launch_attention_fwd(tcq, tckv, ap, num_sms(), st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "column attention launch");
     memset(&g, 0, sizeof g);
     g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
-    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.v2 ? &am.x_out : nullptr, g, st, T_OUT);
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT);
     if (rc) return rc;
     // ---------------- feed-forward (modules.py:213-214, 413-418) ----------------
     {
@@ -829,11 +813,11 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     if (e != cudaSuccess) return fail_cuda(e, "ffn layernorm");
     memset(&g, 0, sizeof g);
     g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
-    rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.v2 ? &am.h : nullptr, g, st, T_FC1);
+    rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.h, g, st, T_FC1);
     if (rc) return rc;
     memset(&g, 0, sizeof g);
     g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.v2 ? &am.x_out : nullptr, g, st, T_FC2);
+    rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2);
     if (rc) return rc;
   }
   return ESMB200_OK;
@@ -904,9 +888,24 @@ int esmb200_debug_read_attn_trace(long long* out, int32_t n) {
 }
 #endif
 
-long long esmb200_launch_count(void) { return g_prof.launches; }
+int esmb200_set_option(const char* name, int32_t value) {
+  if (!name) return fail(ESMB200_EINVAL, "null option name");
+  if (!strcmp(name, "attn") && (value == 7 || value == 8)) { g_attn_version = value; return ESMB200_OK; }
+  if (!strcmp(name, "attn_poly") && (value == 0 || value == 2 || value == 3 || value == 4)) {
+    g_attn_poly = value;
+    return ESMB200_OK;
+  }
+  if (!strcmp(name, "pdl") && (value == 0 || value == 1)) { pdl_flag() = value; return ESMB200_OK; }
+  return fail(ESMB200_EINVAL, std::string("unknown option or value: ") + name);
+}
+
+long long esmb200_launch_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  return g_prof.launches;
+}
 
 int esmb200_profile_enable(int32_t max_launches) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
   g_prof.ev.clear();
   g_prof.tag.clear();
@@ -921,6 +920,7 @@ int esmb200_profile_enable(int32_t max_launches) {
 }
 
 int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records) {
+  std::lock_guard<std::mutex> lk(g_prof.mu);
   const int n = (int)(g_prof.used / 2);
   int out = 0;
   for (int i = 0; i < n && out < max_records; ++i, ++out) {

@@ -1,6 +1,6 @@
 // esm_b200 — attention forward v7 (sm_100a, head_dim 64): v4's persistent pipeline with TWO tcgen05.mma issuing threads.
 //
-// Replaces /root/reference/esm/multihead_attention.py:357-394 (same contract as attention.cuh).
+// Replaces /root/reference/esm/multihead_attention.py:357-394 (contract: attention_common.cuh).
 //
 // Measured on B200 (profiles/r01_attention_decomposition.txt): one issuing thread is a serial stream of ~130 cycles per
 // tcgen05.mma whatever N is, and v4 issues the 4 Q.K^T and the 4 P.V instructions of every 64-key block from one thread —
@@ -12,7 +12,7 @@
 // disabled v7 runs in 0.49 ms where v4 needs 0.63 ms — but with them the softmax warps are now the bottleneck at the same
 // ~1560 cycles per block (two CTAs' exponential passes saturate the SM's MUFU pipe, ~80 % of its mixed-instruction rate),
 // so the full kernel is only 1 % faster than v4; moving a quarter of the exponentials to the FMA pipe (exp2_fma below)
-// and packed FFMA2/FADD2 arithmetic bring it to 0.577 ms (595 TFLOP/s, +8 % over v4).  This is the default kernel; ESMB200_ATTN=4 selects v4.
+// and packed FFMA2/FADD2 arithmetic bring it to 0.577 ms (595 TFLOP/s, +8 % over v4).  Superseded as the default by attention8.cuh; ESMB200_ATTN=7 selects it for A/B runs.
 // To keep the hand-offs to one barrier per direction, P_g is stored over the first 32 columns of its own S_g buffer
 // (every softmax thread has read its whole S row into registers before it writes P), so
 //   * Q.K^T(g+3), which overwrites S buffer g%3, is gated by pv_done(g) alone — that also implies S_g was read;
@@ -25,48 +25,9 @@
 // TMEM (256 columns, 2 CTAs/SM): S0/P0 [0,64) S1/P1 [64,128) S2/P2 [128,192) | O [192,256).
 #pragma once
 
-#include "attention.cuh"
-#include "attention2.cuh"
-#include "attention4.cuh"
-#include "common.cuh"
+#include "attention_common.cuh"
 
 namespace esmb200 {
-
-// 2^x on the FMA pipe (Cody-Waite range reduction + cubic minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5,
-// well below the fp16 rounding of P): used for one pair of keys in ESMB200_ATTN_POLY to take load off the MUFU pipe,
-// which bounds this kernel (16 ex2/clk/SM).  x <= ~12 here; very negative x is clamped to 2^-126 (rounds to 0 in fp16).
-__device__ __forceinline__ float exp2_fma(float x) {
-  x = fmaxf(x, -126.0f);
-  const float r = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of r hold round(x)
-  const float f = x - (r - 12582912.0f);    // in [-0.5, 0.5]
-  float p = fmaf(f, 0.0551716685f, 0.2426111251f);
-  p = fmaf(p, f, 0.6932609677f);
-  p = fmaf(p, f, 0.9999280572f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
-}
-
-// Every ESMB200_ATTN_POLY-th pair of keys takes the FMA-pipe exponential (0 = none).  Measured at B=64 (ms per launch),
-// scalar arithmetic: 0: 0.615, 4 (25 %): 0.594, 3 (37.5 %): 0.651, 2 (50 %): 0.658; with the packed FFMA2/FADD2 forms used
-// now: 0: 0.621, 4: 0.577, 3: 0.593, 2: 0.618 — beyond a quarter the extra ALU/FMA instructions cost more than the MUFU
-// cycles they save (the SM's issue slots are ~60 % busy in this kernel, profiles/r01_ncu_attention_v7_and_tied.txt).
-// the same for two values at once with packed FFMA2 / FADD2 arithmetic
-__device__ __forceinline__ void exp2_fma_pair(float x0, float x1, float& p0, float& p1) {
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  float r0, r1, n0, n1, f0, f1;
-  add2(r0, r1, x0, x1, 12582912.0f, 12582912.0f);
-  add2(n0, n1, r0, r1, -12582912.0f, -12582912.0f);
-  fma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);
-  fma2(p0, p1, f0, f1, 0.0551716685f, 0.0551716685f, 0.2426111251f, 0.2426111251f);
-  fma2(p0, p1, p0, p1, f0, f1, 0.6932609677f, 0.6932609677f);
-  fma2(p0, p1, p0, p1, f0, f1, 0.9999280572f, 0.9999280572f);
-  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
-  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
-}
-
-#ifndef ESMB200_ATTN_POLY
-#define ESMB200_ATTN_POLY 4
-#endif
 
 namespace attn7_cfg {
 using namespace attn4_cfg;
@@ -127,6 +88,8 @@ attention_fwd_kernel_v7(const __grid_constant__ CUtensorMap tmap_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything below reads the previous kernel's output or writes ctx
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;        // + 64 * buffer; P_g occupies the first 32 columns of S_g's buffer
   const uint32_t tmem_o = tmem_base + 192;
@@ -313,7 +276,7 @@ attention_fwd_kernel_v7(const __grid_constant__ CUtensorMap tmap_q, const __grid
           rsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
           if (j == 0 || trip == 1) break;
           const float bmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-          const bool raise = bmax > m_ref + attn2_cfg::RESCALE_TAU;
+          const bool raise = bmax > m_ref + attn_cfg::RESCALE_TAU;
           if (!__any_sync(0xffffffffu, raise)) break;
           // rare: raise the reference of this warp's rows, rescale O (TMEM) and the row sum, redo the block.
           // S_g is still intact: P_g has not been stored over it yet.
@@ -388,17 +351,12 @@ attention_fwd_kernel_v7(const __grid_constant__ CUtensorMap tmap_q, const __grid
 inline cudaError_t launch_attention_v7(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const AttnParams& p,
                                        int num_sms, cudaStream_t stream) {
   using namespace attn4_cfg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(attention_fwd_kernel_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
   const int grid = (int)(total < 2LL * num_sms ? total : 2LL * num_sms);
-  attention_fwd_kernel_v7<<<grid, attn7_cfg::NUM_THREADS7, SMEM_BYTES, stream>>>(tmap_q, tmap_kv, p);
-  return cudaGetLastError();
+  return launch_pdl(attention_fwd_kernel_v7, dim3(grid), dim3(attn7_cfg::NUM_THREADS7), SMEM_BYTES, stream, tmap_q,
+                    tmap_kv, p);
 }
 
 }  // namespace esmb200

@@ -1,0 +1,356 @@
+// esm_b200 — attention forward v8 (sm_100a, head_dim 64): FOUR small persistent CTAs per SM.
+//
+// Replaces /root/reference/esm/multihead_attention.py:357-394 (same contract as attention7.cuh).
+//
+// Why (profiles/r01_ncu_attention_v7_and_tied.txt): v7 (2 CTAs/SM, S triple buffered, two MMA
+// issuing threads) leaves every unit idle — tensor pipe 26 %, MUFU 40 %, issue slots 61 % — because only TWO softmax
+// warps live on each SM sub-partition and each of them serialises  mbarrier wait -> tcgen05.ld -> exp pass ->
+// tcgen05.st -> arrive  (~470 of ~1560 cycles per 64-key block are latency, not work).  v8 hides that latency with
+// occupancy instead of buffering:
+//   * 4 CTAs per SM (192 threads, 128 TMEM columns, ~50 KB smem each) -> FOUR softmax warps per sub-partition, each
+//     belonging to a different CTA / query tile, so some warp is always in its exponential pass;
+//   * per CTA the pipeline is strictly serial and needs ONE S buffer:  QK^T(j) -> softmax(j) -> [P.V(j); QK^T(j+1)];
+//     P_j (fp16) is stored over the first 32 columns of S_j and QK^T(j+1) is issued right behind P.V(j) by the same
+//     thread: tcgen05.mma instructions of one thread execute in issue order, so the overwrite of S/P cannot pass the
+//     read of P (define ESMB200_ATTN8_SAFE_WAR to add an explicit commit/wait between them);
+//   * the commit that signals S_{j+1} also covers P.V(j): when a softmax thread holds S_{j+1}, O already contains block
+//     j, so the rare reference-max raise rescales O without a further barrier, and no o_free hand-off is needed either
+//     (the first P.V of the next tile is gated by p_full, which every thread arrives on after it has read O);
+//   * fewer instructions per key: the block maximum is no longer tracked.  P = exp(s - m_ref) against a lazily raised
+//     reference; a block whose ROW SUM exceeds 2^12 (or is not finite) is the signal that m_ref must be raised — the
+//     row sum is needed anyway, the 64 FMNMX per row and block are gone (they were ~1/6 of the issue slots).
+// Exactness: softmax is invariant to the reference, P is rounded to fp16 relative to it (values <= 2^12 keep the full
+// 11-bit significand), row sums and O are fp32.
+//
+// TMEM (128 columns per CTA, 4 CTAs/SM = all 512): S/P [0,64) | O [64,128).
+#pragma once
+
+#include "attention_common.cuh"
+
+namespace esmb200 {
+
+namespace attn8_cfg {
+constexpr int BLOCK_Q = 128;
+constexpr int BLOCK_KV = 64;
+constexpr int HEAD_DIM = 64;
+constexpr int KV_STAGES = 2;
+constexpr int Q_BYTES = 128 * 64 * 2;  // 16 KB
+constexpr int KV_BYTES = 64 * 64 * 2;  // 8 KB per K tile and per V tile
+constexpr int NUM_THREADS = 192;       // warp 0 TMA, warp 1 MMA issuer + TMEM owner, warps 2-5 softmax (thread = query row)
+constexpr int CTAS_PER_SM = 4;
+constexpr int TMEM_COLS = 128;
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 1024 + 128;
+constexpr float SUM_LIMIT = 4096.0f;   // raise the reference when a block's row sum exceeds this
+}  // namespace attn8_cfg
+
+// exp2 of the 32 scores in sv (already in registers) against the reference mneg = -m_ref * log2(e); returns the packed
+// fp16 probabilities in pk[16] and adds the fp32 row sum into sum[4].  POLY: every POLY-th pair takes the FMA pipe.
+template <int POLY>
+__device__ __forceinline__ void attn8_exp_half(const uint32_t (&sv)[32], uint32_t wd, float mneg, float (&sum)[4],
+                                               uint32_t (&pk)[16]) {
+  constexpr float LOG2E = attn_cfg::LOG2E;
+  if (wd == 0xFFFFFFFFu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float s0 = __uint_as_float(sv[2 * i]), s1 = __uint_as_float(sv[2 * i + 1]);
+      float x0, x1, p0, p1;
+      fma2(x0, x1, s0, s1, LOG2E, LOG2E, mneg, mneg);
+      if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == 0) {
+        exp2_fma_pair(x0, x1, p0, p1);
+      } else {
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      add2(sum[(i & 1) * 2], sum[(i & 1) * 2 + 1], sum[(i & 1) * 2], sum[(i & 1) * 2 + 1], p0, p1);
+      pk[i] = pack_half2(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const bool k0 = (wd >> (2 * i)) & 1u, k1 = (wd >> (2 * i + 1)) & 1u;
+      const float s0 = k0 ? __uint_as_float(sv[2 * i]) : -INFINITY;
+      const float s1 = k1 ? __uint_as_float(sv[2 * i + 1]) : -INFINITY;
+      const float p0 = ex2_approx(fmaf(s0, LOG2E, mneg));  // ex2(-inf) = 0 for masked keys
+      const float p1 = ex2_approx(fmaf(s1, LOG2E, mneg));
+      sum[i & 3] += p0 + p1;
+      pk[i] = pack_half2(p0, p1);
+    }
+  }
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, attn8_cfg::CTAS_PER_SM)
+attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                        const AttnParams p) {
+  using namespace attn8_cfg;
+  constexpr float LOG2E = attn_cfg::LOG2E;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem + Q_BYTES;                         // KV_STAGES buffers
+  uint8_t* smem_v = smem + Q_BYTES + KV_STAGES * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + KV_STAGES * 2 * KV_BYTES);
+  uint64_t* q_full = bars;         // [1] TMA -> MMA
+  uint64_t* q_empty = bars + 1;    // [1] MMA -> TMA (every QK^T of the tile has completed)
+  uint64_t* kv_full = bars + 2;    // [2] TMA -> MMA
+  uint64_t* kv_empty = bars + 4;   // [2] MMA -> TMA (2 arrivals: K released by QK^T, V by P.V)
+  uint64_t* s_full = bars + 6;     // [1] MMA -> softmax: S_j written (and P.V(j-1) accumulated)
+  uint64_t* p_full = bars + 7;     // [1] softmax -> MMA: P_j stored (128 arrivals)
+  uint64_t* o_full = bars + 8;     // [1] MMA -> softmax: last P.V of the tile accumulated
+  uint64_t* pv_done = bars + 9;    // [1] ESMB200_ATTN8_SAFE_WAR only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const uint32_t warp = threadIdx.x / 32;
+  const uint32_t lane = threadIdx.x % 32;
+  const int nqt = (p.T + BLOCK_Q - 1) / BLOCK_Q;
+  const int total = p.B * p.H * nqt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything below reads the previous kernel's output (qkv, key bits) or writes ctx
+  const uint32_t tmem_s = *tmem_slot;  // P_j occupies the first 32 columns of S_j
+  const uint32_t tmem_o = tmem_s + 64;
+
+  auto n_blocks = [&](int w) -> int {
+    const int b = w / (nqt * p.H);
+    return (p.kvlen[b] + BLOCK_KV - 1) / BLOCK_KV;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t g = 0, tq = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int nblk = n_blocks(w);
+        if (nblk == 0) continue;
+        const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
+        const int row_base = (b / p.cols) * p.T;
+        const int x0 = (b % p.cols) * 3 * p.E + h * HEAD_DIM;
+        mbar_wait_relaxed(q_empty, (tq & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(smem_q, &tmap_q, q_full, x0, row_base + qt * BLOCK_Q);
+        for (int i = 0; i < nblk; ++i, ++g) {
+          const uint32_t s = g % KV_STAGES;
+          mbar_wait_relaxed(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+          tma_load_2d(smem_k + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E, row_base + i * BLOCK_KV);
+          tma_load_2d(smem_v + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E, row_base + i * BLOCK_KV);
+        }
+        ++tq;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: QK^T(0), then [P.V(j); QK^T(j+1)] per block =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 64, false);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, true);
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q), 1024, 0);
+      uint32_t g = 0, tq = 0, np = 0;
+      auto issue_qk = [&](uint32_t gg, bool last) {
+        const uint32_t s = gg % KV_STAGES;
+        mbar_wait(&kv_full[s], (gg / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * KV_BYTES), 1024, 0);
+#pragma unroll
+        for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        tc_commit(s_full);
+        tc_commit(&kv_empty[s]);
+        if (last) tc_commit(q_empty);  // every QK^T of this tile has been issued: Q may be reloaded when they finish
+      };
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int nblk = n_blocks(w);
+        if (nblk == 0) continue;
+        mbar_wait(q_full, tq & 1);
+        issue_qk(g, nblk == 1);
+        for (int j = 0; j < nblk; ++j, ++g, ++np) {
+          const uint32_t s = g % KV_STAGES;
+          mbar_wait(p_full, np & 1);  // P_j stored (and, on the first block of a tile, the previous O read out)
+          tc_fence_after();
+          const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KV_BYTES), 1024, 8192);
+#pragma unroll
+          for (int k = 0; k < BLOCK_KV / 16; ++k)
+            umma_ts(tmem_o, tmem_s + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          tc_commit(&kv_empty[s]);
+#ifdef ESMB200_ATTN8_SAFE_WAR
+          tc_commit(pv_done);
+          mbar_wait(pv_done, np & 1);
+          tc_fence_after();
+#endif
+          if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
+          else tc_commit(o_full);
+        }
+        ++tq;
+      }
+    }
+  } else {
+    // ===================== softmax / output warps (2-5): one thread per query row =====================
+    const uint32_t quarter = warp % 4;
+    const uint32_t row_local = quarter * 32 + lane;
+    const uint32_t lane_addr = (quarter * 32u) << 16;
+    const uint32_t ts = tmem_s + lane_addr;
+    uint32_t ns = 0, nt = 0;  // S blocks / tiles consumed so far (barrier phases)
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
+      const int nblk = n_blocks(w);
+      const int row_base = (b / p.cols) * p.T;
+      const int t = qt * BLOCK_Q + row_local;
+      float m_ref = 0.f, l_run = 0.f;
+      bool seeded = false;  // m_ref holds the exact maximum of the first block that has an attendable key
+      const uint32_t* kb_ptr = p.keybits + (size_t)b * p.words;
+
+      for (int j = 0; j < nblk; ++j, ++ns) {
+        const uint2 kw2 = __ldg(reinterpret_cast<const uint2*>(kb_ptr + j * 2));
+        const uint32_t kw[2] = {kw2.x, kw2.y};
+        mbar_wait(s_full, ns & 1);
+        tc_fence_after();
+        if (!seeded) {  // uniform over the CTA: the key mask is per sequence
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            tmem_ld_32x32b_x32(ts + c * 32, sv);
+            tmem_wait_ld_dep(sv);
+            const uint32_t wd = kw[c];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              mx[i & 3] = fmaxf(mx[i & 3], (wd == 0xFFFFFFFFu || ((wd >> i) & 1u)) ? __uint_as_float(sv[i]) : -INFINITY);
+          }
+          const float m0 = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          if ((kw[0] | kw[1]) != 0u) {
+            m_ref = m0;
+            seeded = true;
+          }
+        }
+
+        float rsum = 0.f;
+        uint32_t pk[2][16];
+        for (int trip = 0;; ++trip) {
+          const float mneg = -m_ref * LOG2E;
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            tmem_ld_32x32b_x32(ts + c * 32, sv);
+            tmem_wait_ld_dep(sv);
+            attn8_exp_half<POLY>(sv, kw[c], mneg, sum, pk[c]);
+          }
+          rsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+          if (trip == 1) break;
+          const bool raise = !(rsum <= SUM_LIMIT);  // also true for inf / NaN (exp overflow)
+          if (!__any_sync(0xffffffffu, raise)) break;
+          // rare: some score of this block lies far above the reference.  Find the block maximum, raise the reference
+          // of this warp's rows, rescale O (P.V(j-1) has completed: the commit behind QK^T(j) covers it) and the row
+          // sum, and redo the block.  S_j is intact: P_j has not been stored over it yet.
+          float bmax = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t sv[32];
+            tmem_ld_32x32b_x32(ts + c * 32, sv);
+            tmem_wait_ld_dep(sv);
+            const uint32_t wd = kw[c];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((wd >> i) & 1u) bmax = fmaxf(bmax, __uint_as_float(sv[i]));
+          }
+          const float m_new = fmaxf(m_ref, bmax);
+          const float alpha = ex2_approx((m_ref - m_new) * LOG2E);
+          if (j > 0) {
+#pragma unroll 1
+            for (int q8 = 0; q8 < 4; ++q8) {
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(tmem_o + lane_addr + q8 * 16, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st_32x32b_x16(tmem_o + lane_addr + q8 * 16, ov);
+            }
+          }
+          l_run *= alpha;
+          m_ref = m_new;
+        }
+        // P_j over the first 32 columns of S_j (this thread's own row, already consumed)
+        tmem_st_32x32b_x16(ts, pk[0]);
+        tmem_st_32x32b_x16(ts + 16, pk[1]);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        l_run += rsum;
+      }
+
+      // ---- tile epilogue: O / l -> ctx
+      uint32_t outv[32];
+      if (nblk > 0) {
+        mbar_wait(o_full, nt & 1);
+        ++nt;
+        tc_fence_after();
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(tmem_o + lane_addr + hlf * 32, ov);
+          tmem_wait_ld_dep(ov);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            outv[hlf * 16 + i] = pack_half2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
+        }
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) outv[i] = 0u;
+      }
+      if (t < p.T) {
+        if (p.row_max != nullptr) {
+          const size_t si = ((size_t)b * p.H + h) * p.T + t;
+          p.row_max[si] = m_ref;
+          p.row_sum[si] = l_run;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * p.E + h * HEAD_DIM);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_s, TMEM_COLS);
+  }
+}
+
+template <int POLY>
+inline cudaError_t launch_attention_v8_poly(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const AttnParams& p,
+                                            int num_sms, cudaStream_t stream) {
+  using namespace attn8_cfg;
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
+  const long long cap = (long long)CTAS_PER_SM * num_sms;
+  const int grid = (int)(total < cap ? total : cap);
+  return launch_pdl(attention_fwd_kernel_v8<POLY>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_q, tmap_kv, p);
+}
+
+}  // namespace esmb200

@@ -10,6 +10,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #ifndef ESMB200_WATCHDOG
 #define ESMB200_WATCHDOG 1   // trap instead of hanging forever on a lost mbarrier arrival
@@ -420,6 +422,46 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, bool b_mn_major) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((n >> 3) << 17) |
          ((m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor on the stream is still draining; everything it does before pdl_wait() (barrier init,
+// TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.  pdl_wait() returns when the predecessor has
+// completed and its memory is visible; both instructions are no-ops in a normal launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// process-wide switch: -1 = not read yet (environment ESMB200_PDL, default on); esmb200_set_option("pdl", v) overrides
+inline int& pdl_flag() {
+  static int flag = -1;
+  return flag;
+}
+inline bool pdl_enabled() {
+  int& f = pdl_flag();
+  if (f < 0) {
+    const char* e = getenv("ESMB200_PDL");
+    f = (e && e[0] == '0') ? 0 : 1;
+  }
+  return f != 0;
+}
+
+// host: launch `kernel` with the PDL attribute (ESMB200_PDL=0 disables it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,11 +16,13 @@ namespace esmb200 {
 // Each lane owns float4 chunks lane, lane+32, ... of the row. MAXV bounds E <= MAXV*128.
 template <int MAXV, bool OUT_HALF>
 __global__ void __launch_bounds__(256)
-layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      void* __restrict__ out, int M, int E, float eps) {
+layernorm_rows_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta, void* out, int M,
+                      int E, float eps) {  // x and out may alias (in-place final LayerNorm): a warp reads its whole row first
   const int warps_per_block = blockDim.x / 32;
   const int row = blockIdx.x * warps_per_block + threadIdx.x / 32;
   if (row >= M) return;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x % 32;
   const int nvec = E / 4;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * E);
@@ -76,11 +78,11 @@ inline cudaError_t launch_layernorm(const float* x, const float* gamma, const fl
   const int wpb = 8;
   const int grid = (M + wpb - 1) / wpb;
   if (grid == 0) return cudaSuccess;
-  if (E <= 4 * 128) layernorm_rows_kernel<4, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
-  else if (E <= 10 * 128) layernorm_rows_kernel<10, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
-  else if (E <= 20 * 128) layernorm_rows_kernel<20, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
-  else layernorm_rows_kernel<40, OUT_HALF><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, out, M, E, eps);
-  return cudaGetLastError();
+  const dim3 g(grid), b(wpb * 32);
+  if (E <= 4 * 128) return launch_pdl(layernorm_rows_kernel<4, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  if (E <= 10 * 128) return launch_pdl(layernorm_rows_kernel<10, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  if (E <= 20 * 128) return launch_pdl(layernorm_rows_kernel<20, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  return launch_pdl(layernorm_rows_kernel<40, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
 }
 
 // One block per sequence: counts <mask>/<pad>, then writes the scaled embedding rows.
@@ -176,6 +178,8 @@ __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __
 // (/root/reference/esm/axial_attention.py:82-85).  qkv [M, 3E] fp16, pad [M] (1 = padding); one warp per row.
 __global__ void __launch_bounds__(256)
 zero_q_at_pads_kernel(__half* __restrict__ qkv, const uint8_t* __restrict__ pad, int M, int E) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + threadIdx.x / 32;
   if (row >= M || !pad[row]) return;
   uint4* q = reinterpret_cast<uint4*>(qkv + (size_t)row * 3 * E);  // E % 64 == 0: E*2 bytes is a multiple of 16

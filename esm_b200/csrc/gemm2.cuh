@@ -11,8 +11,7 @@
 //     never read back into the SM.
 #pragma once
 
-#include "common.cuh"
-#include "gemm.cuh"
+#include "gemm_common.cuh"
 
 namespace esmb200 {
 
@@ -29,8 +28,11 @@ constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;   // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
+constexpr int BOX_M = 128;        // rows of an A-operand TMA box
 constexpr int NUM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue (168 regs/thread:
-                                  // 3 warps per SMSP share its 16 K registers)
+                                  // 3 warps per SMSP share its 16 K registers; setmaxnreg 40/232 was tried — ptxas 12.9
+                                  // then spills the control warps or fails to allocate the epilogue branch)
+constexpr int FIRST_EPI_WARP = 4;
 constexpr int STG_BYTES = 128 * 128;  // 128 rows x 128 B staging tile
 constexpr int NUM_STG = 4;            // 2 per 128-column half
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STG * STG_BYTES + 1024 + 256;
@@ -50,12 +52,11 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
 
 // (a variant writing fp16 rows straight from registers to global memory, without smem staging, measured slower:
 // profiles/r01_epilogue_experiments.txt)
-template <int EPI, bool DIRECT = false>
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   using namespace gemm2_cfg;
-  constexpr bool OUT_F16 = (EPI == EPI_QKV_ROPE || EPI == EPI_BIAS_GELU || EPI == EPI_F16_STOREONLY);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -79,6 +80,21 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BLOCK_K;
+  // Tile walk of this cluster (tile = m_blk * tiles_n + n_blk).  Default: strided — at any moment the clusters cover a few
+  // adjacent 256-row slabs of A and all of B, which keeps a long-K A slab (fc2: 2.6 MB) L2-resident while it is reused.
+  // p.chunked: one contiguous run per cluster, so consecutive tiles share their rows (the RoPE epilogue then reloads
+  // its cos/sin registers once per slab); only for short K, where 74 concurrent A slabs fit the L2.
+  int tile_first, tile_step, tile_count;
+  if (p.chunked) {
+    const int per = num_tiles / num_clusters, rem = num_tiles % num_clusters;
+    tile_first = cluster_id * per + (cluster_id < rem ? cluster_id : rem);
+    tile_count = per + (cluster_id < rem ? 1 : 0);
+    tile_step = 1;
+  } else {
+    tile_first = cluster_id;
+    tile_step = num_clusters;
+    tile_count = cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -103,13 +119,15 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // A (and x for the reduce-add) come from the previous kernel on the stream
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (one lane per CTA) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int tile = tile_first, it = 0; it < tile_count; tile += tile_step, ++it) {
         const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
         const int a_row = m_blk * PAIR_M + rank * BLOCK_M;
         const int b_row = n_blk * BLOCK_N + rank * HALF_N;
@@ -129,7 +147,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t idesc = umma_idesc_f16(PAIR_M, BLOCK_N, false);
       uint32_t stage = 0, phase = 0;
       int iter = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
         const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
@@ -148,9 +166,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue: TMEM -> regs -> swizzled smem -> TMA store / reduce =====================
-    const uint32_t ew = warp - 4;
+    const uint32_t ew = warp - FIRST_EPI_WARP;
     const uint32_t quarter = warp % 4;
     const uint32_t chalf = ew / 4;
     const uint32_t row_local = quarter * 32 + lane;
@@ -158,13 +176,32 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t bar_id = 1 + chalf;
     uint32_t store_iter = 0;
     int iter = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+    [[maybe_unused]] float rc[32], rs[32];  // EPI_QKV_ROPE: cos / sin of this thread's row
+    [[maybe_unused]] int rope_blk = -1;
+    for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
       const int row0 = m_blk * PAIR_M + rank * BLOCK_M;
       const int row = row0 + row_local;
+      if constexpr (EPI == EPI_QKV_ROPE) {  // before the wait: the loads fly while the tile is still being multiplied
+      // cos/sin of this thread's token position, 64 registers, reloaded only when the 256-row slab changes (tiles are
+      // walked n-fastest, so once per tiles_n tiles) — r01 re-read them from L2 for every 64-column head group
+      // (256 B per thread and group, long-scoreboard stalls in the shortest-K GEMM of the layer).
+      if (p.rope_cos != nullptr && m_blk != rope_blk) {
+        rope_blk = m_blk;
+        const int t = (row < p.M) ? (row % p.T) : 0;
+        const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
+        const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
+          rc[4 * j4 + 0] = c.x; rc[4 * j4 + 1] = c.y; rc[4 * j4 + 2] = c.z; rc[4 * j4 + 3] = c.w;
+          rs[4 * j4 + 0] = sn.x; rs[4 * j4 + 1] = sn.y; rs[4 * j4 + 2] = sn.z; rs[4 * j4 + 3] = sn.w;
+        }
+      }
+      }
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + chalf * 128;
       const int col0 = n_blk * BLOCK_N + chalf * 128;
 
@@ -241,51 +278,61 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       } else if constexpr (EPI == EPI_QKV_ROPE) {
-        const int t = (row < p.M) ? (row % p.T) : 0;
+        const bool rope = p.rope_cos != nullptr;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           const int col = col0 + g * 64;
           if (col >= p.N) break;  // uniform over the 4 warps of this column half
-          uint32_t lo[32], hi[32], outv[32];
+          uint32_t lo[32], hi[32];
           tmem_ld_32x32b_x32(taddr0 + g * 64, lo);
           tmem_ld_32x32b_x32(taddr0 + g * 64 + 32, hi);
-          tmem_wait_ld_dep(lo);  // one wait retires both loads
-          reg_fence(hi);
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           const int sect = col / p.E;  // 0 q, 1 k, 2 v
-          const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
-          const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
           const float sc = (sect == 0) ? p.q_scale : 1.0f;
+          tmem_wait_ld_dep(lo);  // one wait retires both loads
+          reg_fence(hi);
+          if (sect < 2 && rope) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
-            const float x1[4] = {__uint_as_float(lo[4 * j4 + 0]) + bl.x, __uint_as_float(lo[4 * j4 + 1]) + bl.y,
-                                 __uint_as_float(lo[4 * j4 + 2]) + bl.z, __uint_as_float(lo[4 * j4 + 3]) + bl.w};
-            const float x2[4] = {__uint_as_float(hi[4 * j4 + 0]) + bh.x, __uint_as_float(hi[4 * j4 + 1]) + bh.y,
-                                 __uint_as_float(hi[4 * j4 + 2]) + bh.z, __uint_as_float(hi[4 * j4 + 3]) + bh.w};
-            float y1[4], y2[4];
-            if (sect < 2 && p.rope_cos != nullptr) {
-              const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
-              const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
+              const float bls[4] = {bl.x, bl.y, bl.z, bl.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float a = x1[e] * sc, b = x2[e] * sc;
-                y1[e] = a * cc[e] - b * ss[e];  // rotary_embedding.py:16-20 with rotate_half = cat(-x2, x1)
-                y2[e] = b * cc[e] + a * ss[e];
+                const int j = 4 * j4 + e;
+                const float a = (__uint_as_float(lo[j]) + bls[e]) * sc, b = (__uint_as_float(hi[j]) + bhs[e]) * sc;
+                lo[j] = __float_as_uint(a * rc[j] - b * rs[j]);  // rotary_embedding.py:16-20, rotate_half = cat(-x2, x1)
+                hi[j] = __float_as_uint(b * rc[j] + a * rs[j]);
               }
-            } else {  // v, or q/k without rotary embedding (MSA axial attention): bias (+ q scale) only
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { y1[e] = x1[e] * sc; y2[e] = x2[e] * sc; }
             }
-            outv[2 * j4 + 0] = pack_half2(y1[0], y1[1]);
-            outv[2 * j4 + 1] = pack_half2(y1[2], y1[3]);
-            outv[16 + 2 * j4 + 0] = pack_half2(y2[0], y2[1]);
-            outv[16 + 2 * j4 + 1] = pack_half2(y2[2], y2[3]);
+          } else {  // v, or q/k without rotary embedding (MSA axial attention): bias (+ q scale) only
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
+              const float bls[4] = {bl.x, bl.y, bl.z, bl.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                lo[j] = __float_as_uint((__uint_as_float(lo[j]) + bls[e]) * sc);
+                hi[j] = __float_as_uint((__uint_as_float(hi[j]) + bhs[e]) * sc);
+              }
+            }
           }
           uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
           if (issuer) tma_store_wait_read<1>();
           named_bar_sync(bar_id, 128);
-          stage_row_sw128(stg, row_local, outv);
+          const uint32_t srow = smem_u32(stg) + row_local * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {  // 8 columns -> one 16-byte chunk of the 128-byte staging row
+            const uint32_t (&src)[32] = c < 4 ? lo : hi;
+            const int o = (c & 3) * 8;
+            const uint32_t addr = srow + (((uint32_t)c ^ (row_local & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(pack_half2(__uint_as_float(src[o + 0]), __uint_as_float(src[o + 1]))),
+                         "r"(pack_half2(__uint_as_float(src[o + 2]), __uint_as_float(src[o + 3]))),
+                         "r"(pack_half2(__uint_as_float(src[o + 4]), __uint_as_float(src[o + 5]))),
+                         "r"(pack_half2(__uint_as_float(src[o + 6]), __uint_as_float(src[o + 7])))
+                         : "memory");
+          }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
           if (issuer && row0 < p.M) {
@@ -294,6 +341,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           ++store_iter;
         }
+#ifdef ESMB200_EXPERIMENTS
       } else if constexpr (EPI == EPI_LD_X16) {  // profiling only: 8 loads of 16 columns
         uint32_t sink = 0;
 #pragma unroll 1
@@ -335,6 +383,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           sink ^= acc[c];
         }
         if (sink == 0x7fffffffu && row == -1) reinterpret_cast<uint32_t*>(p.out)[0] = sink;
+#endif
       } else if constexpr (EPI < EPI_NONE) {
         // one tcgen05.wait::ld per tile and warp (see the fp16 path)
         uint32_t acc4[4][32];
@@ -392,22 +441,16 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI, bool DIRECT = false>
+template <int EPI>
 inline cudaError_t launch_gemm2_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                                     const GemmParams& p, int num_sms, cudaStream_t stream) {
   using namespace gemm2_cfg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<EPI, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   const int tiles = ((p.M + PAIR_M - 1) / PAIR_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_f16_kernel<EPI, DIRECT><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, tout, p);
-  return cudaGetLastError();
+  return launch_pdl(gemm2_f16_kernel<EPI>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, ta, tb, tout, p);
 }
 
 }  // namespace esmb200

@@ -87,6 +87,8 @@ tied_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0) {
@@ -164,6 +166,8 @@ tied_softmax_kernel(const TiedParams p) {
   const long long row = (long long)blockIdx.x * 8 + warp;  // (h*B + b)*C + ci
   const long long rows = (long long)p.H * p.B * p.C;
   if (row >= rows) return;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = (int)((row / p.C) % p.B);
   float* s = p.S + row * p.C;
   const uint8_t* pad = p.key_pad ? p.key_pad + (size_t)b * p.key_pad_stride : nullptr;
@@ -243,6 +247,8 @@ tied_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0) {
@@ -313,34 +319,23 @@ tied_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
 inline cudaError_t launch_tied_scores(const CUtensorMap& tq, const CUtensorMap& tk, const TiedParams& p,
                                       cudaStream_t st) {
   using namespace tied_cfg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tied_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(tied_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   dim3 grid((p.C + S_BM - 1) / S_BM, (p.C + S_BN - 1) / S_BN, p.B * p.H);
-  tied_scores_kernel<<<grid, NUM_THREADS, S_SMEM_BYTES, st>>>(tq, tk, p);
-  return cudaGetLastError();
+  return launch_pdl(tied_scores_kernel, grid, dim3(NUM_THREADS), S_SMEM_BYTES, st, tq, tk, p);
 }
 
 inline cudaError_t launch_tied_softmax(const TiedParams& p, cudaStream_t st) {
   const long long rows = (long long)p.H * p.B * p.C;
-  tied_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(tied_softmax_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, p);
 }
 
 inline cudaError_t launch_tied_pv(const CUtensorMap& tp, const CUtensorMap& tv, const TiedParams& p, cudaStream_t st) {
   using namespace tied_cfg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tied_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(tied_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   dim3 grid((p.C + V_BM - 1) / V_BM, (p.R + V_ROWS - 1) / V_ROWS, p.B * p.H);
-  tied_pv_kernel<<<grid, NUM_THREADS, V_SMEM_BYTES, st>>>(tp, tv, p);
-  return cudaGetLastError();
+  return launch_pdl(tied_pv_kernel, grid, dim3(NUM_THREADS), V_SMEM_BYTES, st, tp, tv, p);
 }
 
 }  // namespace esmb200

@@ -204,6 +204,13 @@ int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records);
 /* fp32 -> fp16 elementwise */
 int esmb200_convert_f16(const float* src, void* dst_f16, size_t n, void* stream);
 
+/* ---- process-wide kernel selection knobs (A/B measurements; the defaults are the product configuration) ----
+ * "attn"      8 (default: attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, 2 CTAs/SM)          env ESMB200_ATTN
+ * "attn_poly" 0 | 2 | 3 (default) | 4: every n-th pair of softmax exponentials on the FMA pipe   env ESMB200_ATTN_POLY
+ * "pdl"       1 (default) | 0: programmatic dependent launch between the layer's kernels        env ESMB200_PDL
+ * Returns ESMB200_EINVAL for an unknown name or value. Not thread-safe against concurrent launches. */
+int esmb200_set_option(const char* name, int32_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,7 +62,10 @@ def main():
         out = torch.zeros(M, N, dtype=out_dtype, device=dev)
         inv = (1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))).to(dev)
         cos, sin = rope_tables(inv, T)
-        ms = timeit(lambda: L.check(lib.esmb200_gemm_f16(epi, P(a), P(wt), P(bias), P(out), M, N, K, P(cos), P(sin), T, E, S())))
+        try:
+            ms = timeit(lambda: L.check(lib.esmb200_gemm_f16(epi, P(a), P(wt), P(bias), P(out), M, N, K, P(cos), P(sin), T, E, S())))
+        except L.Esmb200Error:  # profiling-only epilogue and the library was built without -DESMB200_EXPERIMENTS
+            return
         res[name] = {"ms": ms, "TFLOP/s": 2.0 * M * N * K / ms / 1e9}
         # cuBLAS reference point for the same shape
         ms2 = timeit(lambda: torch.matmul(a, wt.t()))
