@@ -37,6 +37,7 @@ EXPORTS = (
     "esmb200_axial_stack_forward",
     "esmb200_msa_embed",
     "esmb200_contact_accumulate",
+    "esmb200_contact_finalize",
     "esmb200_layernorm_f16",
     "esmb200_convert_f16",
     "esmb200_launch_count",
@@ -45,6 +46,7 @@ EXPORTS = (
     "esmb200_set_option",
 )
 
+ABI_VERSION = 2
 EPI_QKV_ROPE, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU, EPI_BIAS_F32, EPI_BIAS_GELU_F32 = range(5)
 
 
@@ -72,6 +74,7 @@ class LayerWeights(ctypes.Structure):
         ("fc1_bias", c_void_p),
         ("fc2_weight", c_void_p),
         ("fc2_bias", c_void_p),
+        ("head_dim", c_int32),
     ]
 
 
@@ -92,7 +95,7 @@ def _declare(lib):
     lib.esmb200_layer_destroy.restype = c_int32
     lib.esmb200_layer_destroy.argtypes = [c_void_p]
     lib.esmb200_workspace_bytes.restype = c_size_t
-    lib.esmb200_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    lib.esmb200_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
     lib.esmb200_layer_forward.restype = c_int32
     lib.esmb200_layer_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]
@@ -138,8 +141,11 @@ def _declare(lib):
     lib.esmb200_msa_embed.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_float,
                                       c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.esmb200_contact_accumulate.restype = c_int32
-    lib.esmb200_contact_accumulate.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                               c_int32, c_int32, c_int32, c_void_p]
+    lib.esmb200_contact_accumulate.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.esmb200_contact_finalize.restype = c_int32
+    lib.esmb200_contact_finalize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                             c_void_p]
     lib.esmb200_launch_count.restype = ctypes.c_longlong
     lib.esmb200_launch_count.argtypes = []
     lib.esmb200_profile_enable.restype = c_int32
@@ -163,7 +169,7 @@ def load():
             )
         lib = ctypes.CDLL(LIB_PATH)
         _declare(lib)
-        if lib.esmb200_abi_version() != 1:
+        if lib.esmb200_abi_version() != ABI_VERSION:
             raise Esmb200Error("libesmb200.so ABI version mismatch")
         _lib = lib
     return _lib

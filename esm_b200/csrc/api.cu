@@ -295,15 +295,18 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
 // ---------------------------------------------------------------------------------------------------------------
 struct esmb200_layer {
   int E, H, F;
+  int d;          // head_dim (<= 64); every head occupies a 64-wide slot of the attention-side tensors
+  int Ea;         // 64 * H: width of q / k / v / ctx
+  float q_scale;  // d^-1/2 (multihead_attention.py:100)
   float eps;
   // borrowed fp32 parameters (owned by the caller, must outlive the layer)
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *out_b, *fc1_b, *fc2_b;
   // owned packed copies
-  __half* w_qkv;  // [3E,E]
-  __half* w_out;  // [E,E]
+  __half* w_qkv;  // [3*Ea, E]: row s*Ea + h*64 + slot(j) <- W_s row h*d + j, zero rows elsewhere
+  __half* w_out;  // [E, Ea]: column h*64 + slot(j) <- out_proj.weight column h*d + j
   __half* w_fc1;  // [F,E]
   __half* w_fc2;  // [E,F]
-  float* b_qkv;   // [3E]
+  float* b_qkv;   // [3*Ea]
   CUtensorMap tm_qkv, tm_out, tm_fc1, tm_fc2;  // B operands, box {64, 128 rows}
 };
 
@@ -340,46 +343,71 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   int rc = check_device();
   if (rc) return rc;
   const int E = w->embed_dim, H = w->num_heads, F = w->ffn_dim;
-  if (E <= 0 || H <= 0 || E != H * 64)
-    return fail(ESMB200_EINVAL, "esmb200 supports head_dim == 64 only (embed_dim must equal 64 * num_heads)");
+  if (E <= 0 || H <= 0 || E % H != 0) return fail(ESMB200_EINVAL, "embed_dim must be a positive multiple of num_heads");
+  const int d = w->head_dim > 0 ? w->head_dim : E / H;
+  if (d * H != E || d > 64 || d % 2 != 0)
+    return fail(ESMB200_EINVAL, "esmb200 supports even head_dim <= 64 (ESM-2 8M..3B, MSA Transformer); 15B (128) is not");
+  if (E % 16 != 0) return fail(ESMB200_EINVAL, "embed_dim must be a multiple of 16");
   const bool has_ffn = w->fc1_weight != nullptr;  // NULL fc1_weight: attention-only layer (MSA row-attention sub-layer)
   if (has_ffn && (F <= 0 || F % 64 != 0)) return fail(ESMB200_EINVAL, "ffn_dim must be a positive multiple of 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   esmb200_layer* L = new esmb200_layer();
   memset(static_cast<void*>(L), 0, sizeof(*L));
-  L->E = E; L->H = H; L->F = has_ffn ? F : 0; L->eps = w->ln_eps;
+  const int Ea = 64 * H;
+  L->E = E; L->H = H; L->F = has_ffn ? F : 0; L->d = d; L->Ea = Ea; L->eps = w->ln_eps;
+  L->q_scale = 1.0f / sqrtf((float)d);
   L->ln1_w = w->ln1_weight; L->ln1_b = w->ln1_bias; L->ln2_w = w->ln2_weight; L->ln2_b = w->ln2_bias;
   L->out_b = w->out_bias; L->fc1_b = w->fc1_bias; L->fc2_b = w->fc2_bias;
-  const size_t EE = (size_t)E * E, EF = (size_t)E * F;
+  const size_t EaE = (size_t)Ea * E, EF = (size_t)E * F;
   cudaError_t e;
 #define ALLOC(ptr, bytes)                                              \
   if ((e = cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))) != cudaSuccess) { \
     esmb200_layer_destroy(L);                                          \
     return fail_cuda(e, "cudaMalloc(packed weights)");                 \
   }
-  ALLOC(L->w_qkv, 3 * EE * 2);
-  ALLOC(L->w_out, EE * 2);
+  ALLOC(L->w_qkv, 3 * EaE * 2);
+  ALLOC(L->w_out, EaE * 2);
   if (has_ffn) {
     ALLOC(L->w_fc1, EF * 2);
     ALLOC(L->w_fc2, EF * 2);
   }
-  ALLOC(L->b_qkv, (size_t)3 * E * 4);
+  ALLOC(L->b_qkv, (size_t)3 * Ea * 4);
 #undef ALLOC
-  rc = esmb200_convert_f16(w->q_weight, L->w_qkv, EE, stream);
-  if (!rc) rc = esmb200_convert_f16(w->k_weight, L->w_qkv + EE, EE, stream);
-  if (!rc) rc = esmb200_convert_f16(w->v_weight, L->w_qkv + 2 * EE, EE, stream);
-  if (!rc) rc = esmb200_convert_f16(w->out_weight, L->w_out, EE, stream);
+  if (d == 64) {  // slots are full: plain conversion
+    rc = esmb200_convert_f16(w->q_weight, L->w_qkv, EaE, stream);
+    if (!rc) rc = esmb200_convert_f16(w->k_weight, L->w_qkv + EaE, EaE, stream);
+    if (!rc) rc = esmb200_convert_f16(w->v_weight, L->w_qkv + 2 * EaE, EaE, stream);
+    if (!rc) rc = esmb200_convert_f16(w->out_weight, L->w_out, EaE, stream);
+    if (!rc) {
+      e = cudaMemcpyAsync(L->b_qkv, w->q_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + E, w->k_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + 2 * E, w->v_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) rc = fail_cuda(e, "bias pack");
+    }
+  } else {  // head_dim < 64: scatter every head into its zero-padded 64-wide slot
+    e = cudaMemsetAsync(L->w_qkv, 0, 3 * EaE * 2, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(L->w_out, 0, EaE * 2, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(L->b_qkv, 0, (size_t)3 * Ea * 4, st);
+    if (e != cudaSuccess) rc = fail_cuda(e, "memset(packed weights)");
+    const float* ws3[3] = {w->q_weight, w->k_weight, w->v_weight};
+    const float* bs3[3] = {w->q_bias, w->k_bias, w->v_bias};
+    const unsigned blocks = (unsigned)(((size_t)E * E + 255) / 256);
+    for (int s3 = 0; s3 < 3 && !rc; ++s3) {
+      ProfScope ps(T_CONVERT, st);
+      pack_head_rows_kernel<<<blocks, 256, 0, st>>>(ws3[s3], bs3[s3], L->w_qkv + (size_t)s3 * EaE, L->b_qkv + s3 * Ea, E, d);
+      if ((e = cudaGetLastError()) != cudaSuccess) rc = fail_cuda(e, "pack_head_rows");
+    }
+    if (!rc) {
+      ProfScope ps(T_CONVERT, st);
+      pack_head_cols_kernel<<<blocks, 256, 0, st>>>(w->out_weight, L->w_out, E, Ea, d);
+      if ((e = cudaGetLastError()) != cudaSuccess) rc = fail_cuda(e, "pack_head_cols");
+    }
+  }
   if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc1_weight, L->w_fc1, EF, stream);
   if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc2_weight, L->w_fc2, EF, stream);
-  if (!rc) {
-    e = cudaMemcpyAsync(L->b_qkv, w->q_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + E, w->k_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + 2 * E, w->v_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) rc = fail_cuda(e, "bias pack");
-  }
   const uint32_t wbox = gemm2_cfg::HALF_N;
-  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)E, E, E, wbox);
-  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, E, E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)Ea, E, E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, Ea, Ea, wbox);
   if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
   if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, wbox);
   if (rc) {
@@ -396,13 +424,13 @@ size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T) {
   return attn_scratch_bytes(B, T, 64);
 }
 
-size_t esmb200_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t T) {
-  const size_t M = (size_t)B * T;
+size_t esmb200_workspace_bytes(int32_t E, int32_t H, int32_t F, int32_t B, int32_t T) {
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * H;
   const size_t a = align_up(M * E * 2, 1024);                       // xn fp16 [M,E]
-  const size_t big_qkv_ctx = align_up(M * 3 * E * 2, 1024) + align_up(M * E * 2, 1024);
+  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2, 1024) + align_up(M * Ea * 2, 1024);
   const size_t big_h = align_up(M * F * 2, 1024);
   const size_t big = big_qkv_ctx > big_h ? big_qkv_ctx : big_h;    // h aliases qkv+ctx
-  return a + big + attn_scratch_bytes(B, T, E / 64) + 1024;
+  return a + big + attn_scratch_bytes(B, T, H) + 1024;
 }
 
 namespace {
@@ -414,19 +442,19 @@ struct Workspace {
   AttnScratch as;
 };
 
-int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int F, int B, int T) {
-  if (bytes < esmb200_workspace_bytes(E, F, B, T)) return fail(ESMB200_EWORKSPACE, "workspace too small");
-  const size_t M = (size_t)B * T;
+int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, int F, int B, int T) {
+  if (bytes < esmb200_workspace_bytes(E, H, F, B, T)) return fail(ESMB200_EWORKSPACE, "workspace too small");
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * H;
   uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   ws->xn = reinterpret_cast<__half*>(p);
   p += align_up(M * E * 2, 1024);
   ws->qkv = reinterpret_cast<__half*>(p);
   ws->h = reinterpret_cast<__half*>(p);
-  ws->ctx = reinterpret_cast<__half*>(p + align_up(M * 3 * E * 2, 1024));
-  const size_t big_qkv_ctx = align_up(M * 3 * E * 2, 1024) + align_up(M * E * 2, 1024);
+  ws->ctx = reinterpret_cast<__half*>(p + align_up(M * 3 * Ea * 2, 1024));
+  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2, 1024) + align_up(M * Ea * 2, 1024);
   const size_t big_h = align_up(M * F * 2, 1024);
   p += big_qkv_ctx > big_h ? big_qkv_ctx : big_h;
-  ws->as = carve_attn_scratch(p, B, T, E / 64);
+  ws->as = carve_attn_scratch(p, B, T, H);
   return ESMB200_OK;
 }
 
@@ -438,7 +466,7 @@ struct ActMaps {
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
                        float* attn_probs, long long attn_batch_stride, int attn_flags, const Workspace& ws,
                        const ActMaps& am, cudaStream_t st) {
-  const int E = L->E, F = L->F, H = L->H;
+  const int E = L->E, F = L->F, H = L->H, Ea = L->Ea;
   const int M = B * T;
   cudaError_t e;
   // LN1 -> fp16 (modules.py:124)
@@ -450,8 +478,8 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // q,k,v projections + bias + q scale + RoPE (multihead_attention.py:258-261,354-355)
   GemmParams g;
   memset(&g, 0, sizeof g);
-  g.M = M; g.N = 3 * E; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * E;
-  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f; g.chunked = 1;
+  g.M = M; g.N = 3 * Ea; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * Ea;
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = Ea; g.q_scale = L->q_scale; g.chunked = 1;
   int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
@@ -459,7 +487,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   if (rc) return rc;
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
-  g.M = M; g.N = E; g.K = E; g.bias = L->out_b; g.out = x; g.ldo = E;
+  g.M = M; g.N = E; g.K = Ea; g.bias = L->out_b; g.out = x; g.ldo = E;
   rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
@@ -480,11 +508,12 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   return rc;
 }
 
-int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int F, int M) {
+int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int H, int F, int M) {
+  const uint64_t Ea = (uint64_t)64 * H;
   int rc = make_tmap_f16(&am->xn, ws.xn, M, E, E, gemm2_cfg::BOX_M);
-  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, E, E, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, Ea, Ea, gemm2_cfg::BOX_M);
   if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, F, F, gemm2_cfg::BOX_M);
-  if (!rc) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * (uint64_t)E, 3 * (uint64_t)E, 128);
+  if (!rc) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * Ea, 3 * Ea, 128);
   if (!rc) rc = make_tmap_2d(&am->x_out, x, 4, M, E, E, 128);
   return rc;
 }
@@ -501,15 +530,16 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int E = layers[0]->E, F = layers[0]->F;
+  const int E = layers[0]->E, F = layers[0]->F, H = layers[0]->H;
   if (F <= 0) return fail(ESMB200_EINVAL, "attention-only layers belong to esmb200_axial_stack_forward");
   for (int i = 1; i < n_layers; ++i)
-    if (layers[i]->E != E || layers[i]->F != F) return fail(ESMB200_EINVAL, "layers of one stack must share E and F");
+    if (layers[i]->E != E || layers[i]->F != F || layers[i]->H != H)
+      return fail(ESMB200_EINVAL, "layers of one stack must share E, H and F");
   Workspace ws;
-  rc = carve_workspace(&ws, workspace, workspace_bytes, E, F, B, T);
+  rc = carve_workspace(&ws, workspace, workspace_bytes, E, H, F, B, T);
   if (rc) return rc;
   ActMaps am;
-  rc = make_act_maps(&am, ws, x, E, F, B * T);
+  rc = make_act_maps(&am, ws, x, E, H, F, B * T);
   if (rc) return rc;
   rc = run_key_bits(pad_mask, ws.as, B, T, st);
   if (rc) return rc;
@@ -566,8 +596,9 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
                      int32_t N, int32_t K, const float* rope_cos, const float* rope_sin, int32_t T, int32_t E,
                      void* stream) {
   if (!a || !w || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
-  if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 64 != 0)
-    return fail(ESMB200_EINVAL, "gemm needs K % 64 == 0 and N % 64 == 0");
+  const bool f16_out = (epilogue == EPI_QKV_ROPE || epilogue == EPI_BIAS_GELU);
+  if (M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % (f16_out ? 64 : 32) != 0)
+    return fail(ESMB200_EINVAL, "gemm needs K % 8 == 0 and N % 64 == 0 (fp16 output) / N % 32 == 0 (fp32 output)");
   int rc = check_device();
   if (rc) return rc;
   if (epilogue == EPI_QKV_ROPE && (!rope_cos || !rope_sin || T <= 0 || E <= 0 || E % 64 != 0 || N != 3 * E))
@@ -712,7 +743,7 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
 
 
 size_t esmb200_axial_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t R, int32_t C) {
-  return esmb200_workspace_bytes(E, F, B * C, R) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
+  return esmb200_workspace_bytes(E, E / 64, F, B * C, R) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
 }
 
 // (A CUDA-graph replay of this launch sequence was measured: 20.70 vs 20.77 ms per 128 x 512 MSA — the ~2 ms between the
@@ -738,13 +769,14 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     return fail(ESMB200_EWORKSPACE, "workspace too small");
   const int M = B * R * C;
   Workspace ws;
-  const size_t base_bytes = esmb200_workspace_bytes(E, F, B * C, R);
-  rc = carve_workspace(&ws, workspace, base_bytes, E, F, B * C, R);
+  if (E != 64 * H) return fail(ESMB200_EINVAL, "the MSA axial path needs head_dim 64");
+  const size_t base_bytes = esmb200_workspace_bytes(E, H, F, B * C, R);
+  rc = carve_workspace(&ws, workspace, base_bytes, E, H, F, B * C, R);
   if (rc) return rc;
   uint8_t* tied_scratch = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024)) + base_bytes;
   const size_t tied_bytes = esmb200_tied_row_attention_scratch_bytes(B, C, H);
   ActMaps am;
-  rc = make_act_maps(&am, ws, x, E, F, M);
+  rc = make_act_maps(&am, ws, x, E, H, F, M);
   if (rc) return rc;
   rc = run_key_bits(col_pad_mask, ws.as, B * C, R, st);  // column attention: B*C sequences of R keys
   if (rc) return rc;
@@ -851,8 +883,9 @@ int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const flo
 
 
 int esmb200_contact_accumulate(const float* attn, int64_t batch_stride, const float* w, const uint8_t* keep, float* acc,
-                               float* a1, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi, void* stream) {
-  if (!attn || !w || !acc || !a1) return fail(ESMB200_EINVAL, "null argument");
+                               float* row_sum, float* col_part, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi,
+                               void* stream) {
+  if (!attn || !w || !acc || !row_sum || !col_part) return fail(ESMB200_EINVAL, "null argument");
   const int S = hi - lo;
   if (B <= 0 || H <= 0 || T <= 0 || lo < 0 || hi > T || S <= 0 || B > 65535) return fail(ESMB200_EINVAL, "bad shape");
   if (S > 1024) return fail(ESMB200_EINVAL, "contact head supports at most 1024 positions");
@@ -861,9 +894,23 @@ int esmb200_contact_accumulate(const float* attn, int64_t batch_stride, const fl
   const size_t smem = (size_t)8 * S * sizeof(float);
   dim3 grid((S + 15) / 16, B);  // 8 warps x 2 rows
   if (S <= 512)
-    contact_accumulate_kernel<2, 16, 2><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, a1, H, T, lo, S);
+    contact_accumulate_kernel<2, 16, 2><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, row_sum, col_part, H, T,
+                                                                  lo, S);
   else
-    contact_accumulate_kernel<2, 32, 1><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, a1, H, T, lo, S);
+    contact_accumulate_kernel<2, 32, 1><<<grid, 256, smem, st>>>(attn, batch_stride, w, keep, acc, row_sum, col_part, H, T,
+                                                                  lo, S);
+  CK(cudaGetLastError());
+  return ESMB200_OK;
+}
+
+int esmb200_contact_finalize(const float* acc, const float* u, const float* a1, const float* bias, float* out, int32_t B,
+                             int32_t C, int32_t S, void* stream) {
+  if (!acc || !u || !a1 || !out) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || C <= 0 || S <= 0 || B > 65535) return fail(ESMB200_EINVAL, "bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(T_PROBS, st);
+  dim3 grid((S + 63) / 64, (S + 63) / 64, B);
+  contact_finalize_kernel<<<grid, 256, 0, st>>>(acc, u, a1, bias, out, C, S);
   CK(cudaGetLastError());
   return ESMB200_OK;
 }

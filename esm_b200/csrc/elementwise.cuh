@@ -174,6 +174,29 @@ __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __
   for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
 }
 
+// head_dim < 64: every head's projection rows go to a zero-padded 64-wide slot, first half of the head at slot
+// positions [0, d/2), second half at [32, 32 + d/2) so that the RoPE epilogue's (j, j+32) pairing reproduces the
+// reference's (j, j+d/2) rotate-half pairs (rotary_embedding.py:11-20).  dst must be zero-filled by the caller.
+__device__ __forceinline__ int head_slot(int n, int d) {  // projection output index n = h*d + j -> h*64 + slot(j)
+  const int h = n / d, j = n % d;
+  return h * 64 + (j < d / 2 ? j : 32 + (j - d / 2));
+}
+__global__ void pack_head_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ dst,
+                                      float* __restrict__ bdst, int E, int d) {  // w [E,E] -> dst [64*H, E]
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)E * E) return;
+  const int n = (int)(i / E), k = (int)(i % E);
+  const int r = head_slot(n, d);
+  dst[(size_t)r * E + k] = __float2half_rn(w[i]);
+  if (k == 0) bdst[r] = b[n];
+}
+__global__ void pack_head_cols_kernel(const float* __restrict__ w, __half* __restrict__ dst, int E, int Ea, int d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // w [E,E] (out_proj) -> dst [E, Ea]
+  if (i >= (size_t)E * E) return;
+  const int n = (int)(i / E), k = (int)(i % E);
+  dst[(size_t)n * Ea + head_slot(k, d)] = __float2half_rn(w[i]);
+}
+
 // MSA row attention: q is zeroed at padded positions before the logits are summed over the alignment rows
 // (/root/reference/esm/axial_attention.py:82-85).  qkv [M, 3E] fp16, pad [M] (1 = padding); one warp per row.
 __global__ void __launch_bounds__(256)
@@ -273,18 +296,20 @@ msa_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ e
 // map of channel c = (layer, head),
 //     logit_ij = sum_c w_c (A_c + A_c^T)_ij - sum_c (w_c / a12_c) a1_c[i] a1_c[j] + b,
 //     a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum_i a1_c[i].
-// This kernel reads one layer's maps [B,H,T,T] ONCE and produces  acc[b,i,j] += sum_h w_h A_h[i,j]  and
-// a1[b,h,i] += rowsum + colsum  (a1 zeroed by the caller).  CTA = (16 query rows, batch element b), 8 warps, two CTAs per SM when S <= 512; a warp owns
-// RPW rows, a lane owns the columns lane + 32 k: row sums by warp shuffles, column sums through an [8][S] shared-memory
-// stage and one global atomic per (head, column) and CTA, acc in registers across the head loop (plain read-modify-write:
-// every acc row belongs to exactly one CTA and layers are separate launches).
+// This kernel reads one layer's maps [B,H,T,T] ONCE and produces  acc[b,i,j] += sum_h w_h A_h[i,j],  the row sums
+// row_sum[b,h,i] and per-CTA partial column sums col_part[b,h,tile,j] (tile = 16-row stripe).  CTA = (16 query rows,
+// batch element b), 8 warps, two CTAs per SM when S <= 512; a warp owns RPW rows, a lane owns the columns lane + 32 k:
+// row sums by warp shuffles, column sums through an [8][S] shared-memory stage summed in a fixed order.  No atomics:
+// every output element has exactly one writer and every sum a fixed order, so contacts are bit-reproducible
+// (r01 used float atomicAdd for the column sums).
 template <int RPW, int MAXC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 contact_accumulate_kernel(const float* __restrict__ attn, long long batch_stride, const float* __restrict__ w,
-                          const uint8_t* __restrict__ keep, float* __restrict__ acc, float* __restrict__ a1, int H,
-                          int T, int lo, int S) {
+                          const uint8_t* __restrict__ keep, float* __restrict__ acc, float* __restrict__ row_sum,
+                          float* __restrict__ col_part, int H, int T, int lo, int S) {
   extern __shared__ float s_col[];  // [8][S]
   const int b = blockIdx.y;
+  const int nt = gridDim.x;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int i0 = blockIdx.x * (8 * RPW) + warp * RPW;
   const uint8_t* kp = keep ? keep + (size_t)b * T : nullptr;
@@ -339,7 +364,7 @@ contact_accumulate_kernel(const float* __restrict__ attn, long long batch_stride
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const float t = warp_sum(rs[r]);
-      if (lane == 0 && ki[r] != 0.f) atomicAdd(a1 + ((size_t)b * H + h) * S + i0 + r, t);
+      if (lane == 0 && i0 + r < S) row_sum[((size_t)b * H + h) * S + i0 + r] = t;
     }
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
@@ -347,11 +372,12 @@ contact_accumulate_kernel(const float* __restrict__ attn, long long batch_stride
       if (j < S) s_col[warp * S + j] = colp[c];
     }
     __syncthreads();
+    float* cp = col_part + (((size_t)b * H + h) * nt + blockIdx.x) * S;
     for (int j = threadIdx.x; j < S; j += 256) {
       float t = 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) t += s_col[q * S + j];
-      if (t != 0.f) atomicAdd(a1 + ((size_t)b * H + h) * S + j, t);
+      cp[j] = t;
     }
     __syncthreads();
   }
@@ -363,6 +389,61 @@ contact_accumulate_kernel(const float* __restrict__ attn, long long batch_stride
       for (int c = 0; c < MAXC; ++c) {
         const int j = lane + 32 * c;
         if (j < S) dst[j] += ac[r][c];
+      }
+    }
+  }
+}
+
+// Contact head tail (modules.py:33-41,352-357): contacts[b,i,j] = sigmoid(acc[b,i,j] + acc[b,j,i]
+//   - sum_c u[b,c,i] * a1[b,c,j] + bias),  u = a1 * (w_c / a12_c): the rank-(L*H) APC correction as a 64x64-tiled fp32
+// SIMT product (K = L*H channels, 0.75 GFLOP per 510-residue sequence: too small for the tensor path and needs fp32
+// operands — the correction cancels most of acc), fused with the symmetrisation, bias and sigmoid.  r01 ran this as a
+// cuBLAS sgemm einsum plus four elementwise PyTorch passes.
+__global__ void __launch_bounds__(256)
+contact_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ u, const float* __restrict__ a1,
+                        const float* __restrict__ bias_ptr, float* __restrict__ out, int C, int S) {
+  const float bias = bias_ptr ? __ldg(bias_ptr) : 0.f;
+  __shared__ float su[16][64 + 1], sa[16][64 + 1];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // 16 x 16 threads, 4 x 4 outputs each (i = ty + 16 a, j = tx + 16 c)
+  float r[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[a][c] = 0.f;
+  const float* ub = u + (size_t)b * C * S;
+  const float* ab = a1 + (size_t)b * C * S;
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int cc = e / 64, x = e % 64;
+      const bool okc = c0 + cc < C;
+      su[cc][x] = (okc && i0 + x < S) ? ub[(size_t)(c0 + cc) * S + i0 + x] : 0.f;
+      sa[cc][x] = (okc && j0 + x < S) ? ab[(size_t)(c0 + cc) * S + j0 + x] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      float uu[4], aa[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { uu[a] = su[cc][ty + 16 * a]; aa[a] = sa[cc][tx + 16 * a]; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[a][c] = fmaf(uu[a], aa[c], r[a][c]);
+    }
+    __syncthreads();
+  }
+  const float* accb = acc + (size_t)b * S * S;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty + 16 * a;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx + 16 * c;
+      if (i < S && j < S) {
+        const float z = accb[(size_t)i * S + j] + accb[(size_t)j * S + i] - r[a][c] + bias;
+        out[((size_t)b * S + i) * S + j] = 1.0f / (1.0f + __expf(-z));
       }
     }
   }

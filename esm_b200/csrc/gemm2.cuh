@@ -79,7 +79,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tiles_m = (p.M + PAIR_M - 1) / PAIR_M;
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = p.K / BLOCK_K;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;  // a partial last K slab is zero-filled by TMA on both operands
   // Tile walk of this cluster (tile = m_blk * tiles_n + n_blk).  Default: strided — at any moment the clusters cover a few
   // adjacent 256-row slabs of A and all of B, which keeps a long-K A slab (fc2: 2.6 MB) L2-resident while it is reused.
   // p.chunked: one contiguous run per cluster, so consecutive tiles share their rows (the RoPE epilogue then reloads

@@ -140,7 +140,9 @@ def _finalize(p: _Pending, include, out_dir: pathlib.Path, writer: FileWriter):
             result["bos_representations"] = {layer: t[i].clone() for layer, t in p.host["bos"].items()}
         if p.contacts is not None:
             result["contacts"] = p.contacts[i, :n, :n].clone()
-        writer.put(out_dir / f"{label}.pt", result)
+        path = out_dir / f"{label}.pt"
+        path.parent.mkdir(parents=True, exist_ok=True)  # labels may contain '/' (extract.py:99-101)
+        writer.put(path, result)
     p.keep.clear()
 
 
@@ -150,6 +152,8 @@ def run(args) -> int:
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     model, alphabet = pretrained.load_model_and_alphabet(args.model_location)
+    if getattr(model, "random_init", False):
+        raise RuntimeError("refusing to write embeddings of a random-init model: give --model_location a checkpoint")
     model = model.eval().to(dev)
     n_layers = model.num_layers
     if not all(-(n_layers + 1) <= i <= n_layers for i in args.repr_layers):

@@ -11,7 +11,7 @@ Documented deviations from the reference:
   * `TransformerLayer.forward` returns `attn=None` unless `need_head_weights=True` (the reference always computes a
     head-averaged (B,T,T) map that ESM2.forward discards, modules.py:130 / esm2.py:112-121).
   * MMA operands are fp16 (fp32 accumulate, fp32 residual stream / LayerNorm / softmax); tolerance in DESIGN.md.
-  * head_dim must be 64.
+  * head_dim <= 64 (all ESM-2 checkpoints except 15B); heads narrower than 64 run in zero-padded 64-wide slots.
 """
 from __future__ import annotations
 
@@ -60,10 +60,88 @@ class MultiheadAttention(nn.Module):
 
 
 def rope_tables(inv_freq: torch.Tensor, seq_len: int):
-    """cos/sin [T, d/2] fp32 — rotary_embedding.py:53-59 (the reference's table is this one duplicated on the last dim)."""
+    """cos/sin [T, 32] fp32 — rotary_embedding.py:53-59 (the reference's table is the first d/2 columns duplicated on
+    the last dim); columns >= d/2 (head_dim < 64) are padding the kernels never use."""
+    inv_freq = inv_freq.float()
     t = torch.arange(seq_len, device=inv_freq.device).type_as(inv_freq)
     freqs = torch.einsum("i,j->ij", t, inv_freq)
-    return freqs.cos().contiguous(), freqs.sin().contiguous()
+    cos, sin = freqs.cos(), freqs.sin()
+    if cos.shape[1] < 32:
+        pad = 32 - cos.shape[1]
+        cos, sin = F.pad(cos, (0, pad), value=1.0), F.pad(sin, (0, pad), value=0.0)
+    return cos.contiguous(), sin.contiguous()
+
+
+def _f32(p: torch.Tensor) -> torch.Tensor:
+    """fp32 contiguous view of a parameter (the tensor itself when it already is one)."""
+    t = p.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+class LayerBinding:
+    """The esmb200_layer handle of one transformer block, built from a module that carries the reference's attribute
+    names (self_attn.{q,k,v,out}_proj, self_attn_layer_norm, fc1, fc2, final_layer_norm: modules.py:99-118) — this
+    repo's TransformerLayer or the reference's own esm.modules.TransformerLayer (esm_b200.integration).  Parameters that
+    are not fp32 (model.half(), esmfold.py:59-62) are mirrored to fp32 copies owned by the binding; the handle is
+    re-packed when a parameter is replaced or modified in place."""
+
+    def __init__(self, module: nn.Module):
+        self.module = module
+        a = module.self_attn
+        self.embed_dim = a.q_proj.weight.shape[1]
+        self.attention_heads = a.num_heads
+        self.head_dim = self.embed_dim // self.attention_heads
+        self.ffn_embed_dim = module.fc1.weight.shape[0]
+        if self.head_dim * self.attention_heads != self.embed_dim or self.head_dim > 64 or self.head_dim % 2:
+            raise ValueError("esm_b200 supports even head_dim <= 64 (ESM-2 8M/35M/150M/650M/3B); "
+                             f"got embed_dim={self.embed_dim}, heads={self.attention_heads}")
+        self._handle = None
+        self._key = None
+        self._keep = None
+
+    def _params(self) -> List[torch.Tensor]:
+        m, a = self.module, self.module.self_attn
+        return [m.self_attn_layer_norm.weight, m.self_attn_layer_norm.bias, a.q_proj.weight, a.q_proj.bias,
+                a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias,
+                m.final_layer_norm.weight, m.final_layer_norm.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias]
+
+    def handle(self):
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        if self._handle is not None and key == self._key:
+            return self._handle
+        self.release()
+        for p in ps:
+            if not p.is_cuda:
+                raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: move the model with .cuda(); "
+                                        "there is no CPU fallback")
+        lib = _lib.load()
+        keep = [_f32(p) for p in ps]
+        w = _lib.LayerWeights()
+        w.embed_dim, w.num_heads, w.ffn_dim = self.embed_dim, self.attention_heads, self.ffn_embed_dim
+        w.head_dim = self.head_dim
+        w.ln_eps = self.module.self_attn_layer_norm.eps
+        names = [f[0] for f in _lib.LayerWeights._fields_[4:20]]
+        for n, p in zip(names, keep):
+            setattr(w, n, p.data_ptr())
+        out = ctypes.c_void_p()
+        with torch.cuda.device(keep[0].device):
+            _lib.check(lib.esmb200_layer_create(ctypes.byref(w), _stream(), ctypes.byref(out)))
+        self._handle, self._key, self._keep = out, key, keep  # the library borrows LN weights and biases from `keep`
+        return out
+
+    def release(self):
+        if self._handle is not None:
+            _lib.load().esmb200_layer_destroy(self._handle)
+            self._handle, self._key, self._keep = None, None, None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class TransformerLayer(nn.Module):
@@ -71,8 +149,6 @@ class TransformerLayer(nn.Module):
 
     def __init__(self, embed_dim: int, ffn_embed_dim: int, attention_heads: int):
         super().__init__()
-        if embed_dim != 64 * attention_heads:
-            raise ValueError("esm_b200 supports head_dim == 64 only (embed_dim == 64 * attention_heads)")
         self.embed_dim = embed_dim
         self.ffn_embed_dim = ffn_embed_dim
         self.attention_heads = attention_heads
@@ -81,82 +157,51 @@ class TransformerLayer(nn.Module):
         self.fc1 = nn.Linear(embed_dim, ffn_embed_dim)
         self.fc2 = nn.Linear(ffn_embed_dim, embed_dim)
         self.final_layer_norm = nn.LayerNorm(embed_dim)
-        self._handle = None
-        self._handle_key = None
-
-    # ---- C-ABI handle management -------------------------------------------------------------------------------
-    def _params(self) -> List[torch.Tensor]:
-        a = self.self_attn
-        return [self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias, a.q_proj.weight, a.q_proj.bias,
-                a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias, a.out_proj.weight, a.out_proj.bias,
-                self.final_layer_norm.weight, self.final_layer_norm.bias, self.fc1.weight, self.fc1.bias,
-                self.fc2.weight, self.fc2.bias]
+        self._binding = LayerBinding(self)
 
     def handle(self):
-        """esmb200_layer* for the current parameters; re-packed when a parameter is replaced or modified in place."""
-        ps = self._params()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._handle is not None and key == self._handle_key:
-            return self._handle
-        self.release()
-        for p in ps:
-            if not p.is_cuda:
-                raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: move the model with .cuda(); "
-                                        "there is no CPU fallback")
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise _lib.Esmb200Error("esm_b200 expects contiguous fp32 master parameters")
-        lib = _lib.load()
-        w = _lib.LayerWeights()
-        w.embed_dim, w.num_heads, w.ffn_dim = self.embed_dim, self.attention_heads, self.ffn_embed_dim
-        w.ln_eps = self.self_attn_layer_norm.eps
-        names = [f[0] for f in _lib.LayerWeights._fields_[4:]]
-        for n, p in zip(names, ps):
-            setattr(w, n, p.data_ptr())
-        out = ctypes.c_void_p()
-        with torch.cuda.device(ps[0].device):
-            _lib.check(lib.esmb200_layer_create(ctypes.byref(w), _stream(), ctypes.byref(out)))
-        self._handle, self._handle_key = out, key
-        return out
+        """esmb200_layer* for the current parameters."""
+        return self._binding.handle()
 
     def release(self):
-        if self._handle is not None:
-            _lib.load().esmb200_layer_destroy(self._handle)
-            self._handle, self._handle_key = None, None
-
-    def __del__(self):
-        try:
-            self.release()
-        except Exception:
-            pass
+        self._binding.release()
 
     # ---- reference-facing forward ------------------------------------------------------------------------------
     def forward(self, x, self_attn_mask=None, self_attn_padding_mask=None, need_head_weights=False):
         """x: (T, B, E) like the reference (modules.py:120-122). Returns (x (T,B,E), attn (H,B,T,T) or None)."""
-        if self_attn_mask is not None:
-            raise NotImplementedError("ESM-2 never passes self_attn_mask (esm2.py:112-116)")
-        T, B, E = x.shape
-        xb = x.transpose(0, 1).contiguous().float()  # (B,T,E) batch-major copy, updated in place
-        cos, sin = rope_tables(self.self_attn.rot_emb.inv_freq, T)
-        attn = run_stack([self], xb, self_attn_padding_mask, cos, sin, None, [0] if need_head_weights else [])
-        out = xb.transpose(0, 1).to(x.dtype)
-        if need_head_weights:
-            return out, attn[0].transpose(0, 1).contiguous()  # (B,H,T,T) -> (H,B,T,T), multihead_attention.py:398-400
-        return out, None
+        return layer_forward(self._binding, x, self_attn_mask, self_attn_padding_mask, need_head_weights)
 
 
-_workspaces: Dict[torch.device, torch.Tensor] = {}
+def layer_forward(binding: LayerBinding, x, self_attn_mask=None, self_attn_padding_mask=None, need_head_weights=False):
+    """TransformerLayer.forward (modules.py:120-142) through the C ABI, for any module a LayerBinding wraps."""
+    if self_attn_mask is not None:
+        raise NotImplementedError("ESM-2 never passes self_attn_mask (esm2.py:112-116)")
+    T, B, E = x.shape
+    xb = x.transpose(0, 1).contiguous().float()  # (B,T,E) batch-major copy, updated in place
+    cos, sin = rope_tables(binding.module.self_attn.rot_emb.inv_freq, T)
+    attn = run_stack([binding], xb, self_attn_padding_mask, cos, sin, None, [0] if need_head_weights else [])
+    out = xb.transpose(0, 1).to(x.dtype)
+    if need_head_weights:
+        return out, attn[0].transpose(0, 1).contiguous().to(x.dtype)  # (B,H,T,T) -> (H,B,T,T), multihead_attention.py:398-400
+    return out, None
+
+
+_workspaces: Dict[tuple, torch.Tensor] = {}
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    ws = _workspaces.get(device)
+    """Scratch for one stack call, cached per (device, CUDA stream): calls on different streams never share it, calls
+    on one stream are ordered by the stream (the library is re-entrant across handles and streams)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        _workspaces.pop(device, None)
+        _workspaces.pop(key, None)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
-def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask: Optional[torch.Tensor],
+def run_stack(layers: Sequence, x: torch.Tensor, padding_mask: Optional[torch.Tensor],
               rope_cos: torch.Tensor, rope_sin: torch.Tensor, repr_out: Optional[Dict[int, torch.Tensor]],
               attn_layers: Sequence[int], zero_pad_rows: bool = False):
     """esmb200_stack_forward on x fp32 (B,T,E) in place. repr_out: {layer index (0-based): (B,T,E) tensor to fill}.
@@ -170,7 +215,7 @@ def run_stack(layers: Sequence[TransformerLayer], x: torch.Tensor, padding_mask:
     Fdim, H = layers[0].ffn_embed_dim, layers[0].attention_heads
     with torch.cuda.device(x.device):
         handles = (ctypes.c_void_p * n)(*[l.handle() for l in layers])
-        nbytes = lib.esmb200_workspace_bytes(E, Fdim, B, T)
+        nbytes = lib.esmb200_workspace_bytes(E, H, Fdim, B, T)
         ws = _workspace(nbytes, x.device)
         mask = None
         if padding_mask is not None:
@@ -233,8 +278,8 @@ class RobertaLMHead(nn.Module):
         return F.linear(x, self.weight) + self.bias
 
     def _pack(self):
-        ps = [self.dense.weight, self.weight, self.bias]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        ps = [self.dense.weight, self.weight, self.bias, self.dense.bias, self.layer_norm.weight, self.layer_norm.bias]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
         if self._packed is None or key != self._packed_key:
             E = self.dense.weight.shape[1]
             V = self.weight.shape[0]
@@ -243,7 +288,8 @@ class RobertaLMHead(nn.Module):
             w_out[:V] = self.weight.detach().half()
             b_out = torch.zeros((npad,), dtype=torch.float32, device=self.weight.device)
             b_out[:V] = self.bias.detach().float()
-            self._packed = (self.dense.weight.detach().half().contiguous(), w_out, b_out, V, npad)
+            self._packed = (self.dense.weight.detach().half().contiguous(), w_out, b_out, V, npad,
+                            _f32(self.dense.bias), _f32(self.layer_norm.weight), _f32(self.layer_norm.bias))
             self._packed_key = key
         return self._packed
 
@@ -253,18 +299,18 @@ class RobertaLMHead(nn.Module):
         B, T, E = x_pre.shape
         M = B * T
         dev = x_pre.device
-        w_dense, w_out, b_out, V, npad = self._pack()
+        w_dense, w_out, b_out, V, npad, b_dense, ln2_w, ln2_b = self._pack()
         a16 = torch.empty((M, E), dtype=torch.float16, device=dev)
         _lib.check(lib.esmb200_layernorm_f16(_ptr(x_pre), _ptr(ln_w), _ptr(ln_b), _ptr(a16), M, E, eps, _stream()))
         h = torch.empty((M, E), dtype=torch.float32, device=dev)
-        _lib.check(lib.esmb200_gemm_f16(_lib.EPI_BIAS_GELU_F32, _ptr(a16), _ptr(w_dense), _ptr(self.dense.bias),
+        _lib.check(lib.esmb200_gemm_f16(_lib.EPI_BIAS_GELU_F32, _ptr(a16), _ptr(w_dense), _ptr(b_dense),
                                         _ptr(h), M, E, E, None, None, 0, 0, _stream()))
-        _lib.check(lib.esmb200_layernorm_f16(_ptr(h), _ptr(self.layer_norm.weight), _ptr(self.layer_norm.bias),
+        _lib.check(lib.esmb200_layernorm_f16(_ptr(h), _ptr(ln2_w), _ptr(ln2_b),
                                              _ptr(a16), M, E, self.layer_norm.eps, _stream()))
         logits = torch.empty((M, npad), dtype=torch.float32, device=dev)
         _lib.check(lib.esmb200_gemm_f16(_lib.EPI_BIAS_F32, _ptr(a16), _ptr(w_out), _ptr(b_out), _ptr(logits), M, npad, E,
                                         None, None, 0, 0, _stream()))
-        return logits.view(B, T, npad)[:, :, :V]
+        return logits.view(B, T, npad)[:, :, :V].contiguous()  # [B,T,V] packed like the reference's (esm2.py:129)
 
 
 class ContactPredictionHead(nn.Module):
@@ -286,8 +332,9 @@ class ContactPredictionHead(nn.Module):
         24 GB attention stack of configs[3]): with A_c the eos-masked, cropped map of channel c = (layer, head),
             logit_ij = sum_c w_c (A_c + A_c^T)_ij - sum_c (w_c / a12_c) a1_c[i] a1_c[j] + b,
             a1_c = rowsum(A_c) + colsum(A_c),  a12_c = sum(a1_c).
-        On the GPU every layer's maps are read once by esmb200_contact_accumulate (sum over heads + row/column sums);
-        the rank-(L*H) correction, the symmetrisation and the sigmoid act on [B,S,S] / [B,L*H,S] tensors."""
+        On the GPU every layer's maps are read once by esmb200_contact_accumulate (sum over heads + row/column sums,
+        no atomics: bit-reproducible) and esmb200_contact_finalize fuses the rank-(L*H) correction, the symmetrisation,
+        the bias and the sigmoid."""
         B, L, H, T, _ = attentions.shape
         lo = 1 if self.prepend_bos else 0
         hi = T - 1 if self.append_eos else T
@@ -298,23 +345,26 @@ class ContactPredictionHead(nn.Module):
         lib = _lib.load()
         dev = attentions.device
         keep8 = tokens.ne(self.eos_idx).to(torch.uint8).contiguous() if self.append_eos else None
+        nt = (S + 15) // 16
         acc = torch.zeros((B, S, S), dtype=torch.float32, device=dev)
-        a1 = torch.zeros((L, B, H, S), dtype=torch.float32, device=dev)   # layer-major: one [B,H,S] block per launch
+        a1 = torch.empty((B, L, H, S), dtype=torch.float32, device=dev)
+        row = torch.empty((B, H, S), dtype=torch.float32, device=dev)
+        col = torch.empty((B, H, nt, S), dtype=torch.float32, device=dev)
         wl = w.float().contiguous()
         with torch.cuda.device(dev):
             for l in range(L):
                 _lib.check(lib.esmb200_contact_accumulate(
                     ctypes.c_void_p(attentions.data_ptr() + l * H * T * T * 4), L * H * T * T,
-                    ctypes.c_void_p(wl.data_ptr() + l * H * 4), _ptr(keep8), _ptr(acc),
-                    ctypes.c_void_p(a1.data_ptr() + l * B * H * S * 4), B, H, T, lo, hi, _stream()))
-        a1f = a1.permute(1, 0, 2, 3).reshape(B, L * H, S)
-        a12 = a1f.sum(-1, keepdim=True)                                   # [B, L*H, 1]
-        coef = w.reshape(1, L * H, 1) / a12
-        corr = torch.einsum("bci,bcj->bij", a1f * coef, a1f)
-        logits = acc + acc.transpose(-1, -2) - corr
-        if self.regression.bias is not None:
-            logits = logits + self.regression.bias
-        return self.activation(logits)
+                    ctypes.c_void_p(wl.data_ptr() + l * H * 4), _ptr(keep8), _ptr(acc), _ptr(row), _ptr(col),
+                    B, H, T, lo, hi, _stream()))
+                torch.add(row, col.sum(2), out=a1[:, l])               # a1_c = rowsum + colsum, fixed summation order
+            a1f = a1.view(B, L * H, S)
+            a12 = a1f.sum(-1, keepdim=True)                               # [B, L*H, 1]
+            u = (a1f * (wl.reshape(1, L * H, 1) / a12)).contiguous()
+            bias = _f32(self.regression.bias) if self.regression.bias is not None else None
+            out = torch.empty((B, S, S), dtype=torch.float32, device=dev)
+            _lib.check(lib.esmb200_contact_finalize(_ptr(acc), _ptr(u), _ptr(a1f), bias, _ptr(out), B, L * H, S, _stream()))
+        return out
 
     def _forward_torch(self, tokens, attentions, w, lo, hi):
         """The same formula with PyTorch ops (non-CUDA or non-fp32 inputs; cross-check in the tests)."""
@@ -369,6 +419,7 @@ class ESM2(nn.Module):
         self.emb_layer_norm_after = nn.LayerNorm(embed_dim)
         self.lm_head = RobertaLMHead(embed_dim, self.alphabet_size, self.embed_tokens.weight)
         self._rope_cache = None
+        self._mirrors: Dict[str, tuple] = {}
 
     def _rope_tables(self, T: int):
         inv = self.layers[0].self_attn.rot_emb.inv_freq
@@ -376,6 +427,17 @@ class ESM2(nn.Module):
         if self._rope_cache is None or self._rope_cache[0] != key:
             self._rope_cache = (key,) + rope_tables(inv, T)
         return self._rope_cache[1], self._rope_cache[2]
+
+    def _mirror(self, name: str, p: torch.Tensor) -> torch.Tensor:
+        """fp32 mirror of a non-fp32 parameter (model.half()), cached until the parameter changes."""
+        if p.dtype == torch.float32 and p.is_contiguous():
+            return p.detach()
+        key = (p.data_ptr(), p._version, p.dtype)
+        hit = self._mirrors.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, _f32(p))
+            self._mirrors[name] = hit
+        return hit[1]
 
     @torch.no_grad()
     def forward(self, tokens, repr_layers=[], need_head_weights=False, return_contacts=False):
@@ -385,24 +447,32 @@ class ESM2(nn.Module):
         if not tokens.is_cuda:
             raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: pass tokens.cuda(); no CPU fallback")
         lib = _lib.load()
+        if tokens.dtype != torch.int64:
+            if tokens.dtype.is_floating_point or tokens.dtype == torch.bool:
+                raise TypeError(f"tokens must be an integer tensor, got {tokens.dtype}")
+            tokens = tokens.long()
         tokens = tokens.contiguous()
+        # nn.Embedding raises a device-side assert on an out-of-range id (esm2.py:84); same here, without a host sync
+        torch._assert_async(((tokens >= 0) & (tokens < self.alphabet_size)).all())
         B, T = tokens.shape
         E, N = self.embed_dim, self.num_layers
+        dtype = self.embed_tokens.weight.dtype  # fp32, or fp16/bf16 after model.half() (esmfold.py:59-62)
         padding_mask = tokens.eq(self.padding_idx)  # esm2.py:82
         repr_layers = set(repr_layers)
         hidden: Dict[int, torch.Tensor] = {}
+        cast = (lambda t: t) if dtype == torch.float32 else (lambda t: t.to(dtype))
 
         with torch.cuda.device(tokens.device):
             # esm2.py:84-95 embedding prologue
             x = torch.empty((B, T, E), dtype=torch.float32, device=tokens.device)
-            _lib.check(lib.esmb200_embed_tokens(_ptr(tokens), _ptr(self.embed_tokens.weight), _ptr(x), B, T, E,
+            table = self._mirror("embed_tokens", self.embed_tokens.weight)
+            _lib.check(lib.esmb200_embed_tokens(_ptr(tokens), _ptr(table), _ptr(x), B, T, E,
                                                 self.padding_idx, self.mask_idx, int(self.token_dropout), _stream()))
             if 0 in repr_layers:
-                hidden[0] = x.clone()
+                hidden[0] = cast(x.clone())
             # esm2.py:108-109 drops the mask when the batch has no padding; that test is a device->host sync, which
             # would serialise back-to-back forwards (bulk extraction). The kernels take the all-false mask at no cost
-            # (one uniform compare per 32 keys), so the mask is always passed and the sync is only paid on the
-            # need_head_weights path below, where the reference's result depends on it.
+            # (one uniform compare per 32 keys), so the mask is always passed.
             mask = padding_mask
             # esm2.py:111-121 layer loop (intermediate representations are copied out by the library)
             repr_out = {i - 1: torch.empty_like(x) for i in repr_layers if 0 < i < N}
@@ -410,24 +480,24 @@ class ESM2(nn.Module):
             attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out,
                                list(range(N)) if need_head_weights else [], zero_pad_rows=True)
             for i, t in repr_out.items():
-                hidden[i + 1] = t
+                hidden[i + 1] = cast(t)
             # esm2.py:129 LM head, from the pre-LN stream (its first step is the same emb_layer_norm_after)
             ln = self.emb_layer_norm_after
-            logits = self.lm_head.forward_native(x, ln.weight, ln.bias, ln.eps)
+            ln_w, ln_b = self._mirror("ln_after.w", ln.weight), self._mirror("ln_after.b", ln.bias)
+            logits = cast(self.lm_head.forward_native(x, ln_w, ln_b, ln.eps))
             # esm2.py:123-128 final LayerNorm; the last representation is post-LN
-            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(ln.weight), _ptr(ln.bias), _ptr(x), B * T, E, ln.eps,
-                                             _stream()))
+            _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(x), B * T, E, ln.eps, _stream()))
         if N in repr_layers:
-            hidden[N] = x
+            hidden[N] = cast(x)
         result = {"logits": logits, "representations": hidden}
         if need_head_weights:
             # B x L x H x T x T (esm2.py:134), each layer written in place by the library; rows/columns of padded
             # tokens are already zero (esm2.py:135-139: padded keys have probability 0, padded query rows are zeroed
             # by the probability kernel), so no masking pass over the stack is needed
             attentions = attn_t["stacked"]
-            result["attentions"] = attentions
+            result["attentions"] = cast(attentions)
             if return_contacts:
-                result["contacts"] = self.contact_head(tokens, attentions)
+                result["contacts"] = cast(self.contact_head(tokens, attentions))
         return result
 
     def predict_contacts(self, tokens):

@@ -17,7 +17,7 @@
  *     scripts/fold.py:165-178's handler keeps working
  *   - activations: residual stream x is fp32 [B, T, E] row-major (batch-major, i.e. the reference's (T,B,E)
  *     transposed); MMA operands are fp16 with fp32 accumulation; LayerNorm / softmax / residual adds are fp32
- *   - head_dim must be 64 (ESM-2 650M / 3B and the 6/12/30-layer test configs with E = 64*H); no CPU fallback
+ *   - head_dim <= 64 (every esm.pretrained.esm2_* model except the 15B one, whose heads are 128 wide); no CPU fallback
  */
 #ifndef ESMB200_H_
 #define ESMB200_H_
@@ -35,7 +35,7 @@ extern "C" {
 #define ESMB200_ENOMEM -3   /* device allocation failed ("CUDA out of memory ...") */
 #define ESMB200_EWORKSPACE -4 /* workspace too small */
 
-#define ESMB200_ABI_VERSION 1
+#define ESMB200_ABI_VERSION 2
 
 typedef struct esmb200_layer esmb200_layer; /* opaque: packed weights + TMA descriptors of one TransformerLayer */
 
@@ -43,7 +43,7 @@ typedef struct esmb200_layer esmb200_layer; /* opaque: packed weights + TMA desc
  * prefix "layers.{i}."; /root/reference/esm/modules.py:99-118, multihead_attention.py:109-113) */
 typedef struct esmb200_layer_weights {
   int32_t embed_dim;   /* E */
-  int32_t num_heads;   /* H, E == 64*H */
+  int32_t num_heads;   /* H, E == head_dim * H */
   int32_t ffn_dim;     /* F = 4E */
   float ln_eps;        /* 1e-5 */
   const float* ln1_weight; /* self_attn_layer_norm.weight [E] */
@@ -62,6 +62,8 @@ typedef struct esmb200_layer_weights {
   const float* fc1_bias;   /* fc1.bias   [F]   */
   const float* fc2_weight; /* fc2.weight [E,F] */
   const float* fc2_bias;   /* fc2.bias   [E]   */
+  int32_t head_dim;        /* 0 = E / H. Even values <= 64: 16 / 24 / 32 (ESM-2 8M / 35M / 150M) run in zero-padded
+                            * 64-wide head slots of the attention-side tensors; 64 = 650M / 3B / MSA Transformer */
 } esmb200_layer_weights;
 
 int esmb200_abi_version(void);
@@ -73,14 +75,15 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
 int esmb200_layer_destroy(esmb200_layer* layer);
 
 /* Scratch bytes needed by esmb200_layer_forward / esmb200_stack_forward for a [B,T] batch. */
-size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t ffn_dim, int32_t B, int32_t T);
+size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t num_heads, int32_t ffn_dim, int32_t B, int32_t T);
 
 /* One TransformerLayer.forward (modules.py:120-142), in place on x:
  *     x += out_proj(attention(rope(q_proj(LN1 x) * d^-1/2), rope(k_proj(LN1 x)), v_proj(LN1 x)));
  *     x += fc2(gelu(fc1(LN2 x)))
  *   x          fp32 [B,T,E], updated in place
  *   pad_mask   uint8/bool [B,T], nonzero = padding key (self_attn_padding_mask, esm2.py:82), or NULL
- *   rope_cos/sin fp32 [T,32]: cos/sin(t * inv_freq[j]) (rotary_embedding.py:47-61), built by the caller
+ *   rope_cos/sin fp32 [T,32]: cos/sin(t * inv_freq[j]) for j < head_dim/2 (rotary_embedding.py:47-61), built by the
+ *              caller; columns >= head_dim/2 are ignored
  *   attn_probs fp32 [B,H,T,T] or NULL: softmax probabilities per head (need_head_weights=True,
  *              multihead_attention.py:397-400, batch-major i.e. already transposed as esm2.py:121 does) */
 int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mask, int32_t B, int32_t T,
@@ -179,11 +182,20 @@ int esmb200_msa_embed(const int64_t* tokens, const float* embed_table, const flo
 /* Contact head, one layer's share (ContactPredictionHead.forward esm/modules.py:338-357, symmetrize :27-29, apc :32-41):
  * attn = that layer's attention maps fp32 [B,H,T,T] (batch_stride floats between batch elements, so a slice of a stacked
  * [B,L,H,T,T] tensor works), cropped to positions [lo,hi) and multiplied by keep[b,i]*keep[b,j] (keep [B,T], 1 = not
- * <eos>; NULL = no masking). Adds sum_h w[h]*A_h to acc [B,S,S] and rowsum(A_h)+colsum(A_h) to a1 [B,H,S] (S = hi-lo;
- * the caller zeroes both before the first layer); the caller finishes with
- * sigmoid(acc + acc^T - sum_c (w_c/sum_i a1_c[i]) a1_c a1_c^T + bias). */
+ * <eos>; NULL = no masking). S = hi - lo.
+ *   acc      [B,S,S]            += sum_h w[h] * A_h   (zeroed by the caller before the first layer)
+ *   row_sum  [B,H,S]             = rowsum(A_h)
+ *   col_part [B,H,ceil(S/16),S]  = column sums of each 16-row stripe; colsum(A_h) = sum over the stripe axis
+ * No atomics: results are bit-reproducible. a1_c = row_sum + colsum feeds esmb200_contact_finalize. */
 int esmb200_contact_accumulate(const float* attn, int64_t batch_stride, const float* w, const uint8_t* keep, float* acc,
-                               float* a1, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi, void* stream);
+                               float* row_sum, float* col_part, int32_t B, int32_t H, int32_t T, int32_t lo, int32_t hi,
+                               void* stream);
+
+/* Contact head tail (modules.py:33-41,352-357): out[b,i,j] = sigmoid(acc[b,i,j] + acc[b,j,i] - sum_c u[b,c,i]*a1[b,c,j] + bias)
+ * with a1 [B,C,S] (C = layers*heads channels) and u = a1 * w_c / sum_i a1_c[i] prepared by the caller; bias = device
+ * pointer to one float or NULL; out [B,S,S]. */
+int esmb200_contact_finalize(const float* acc, const float* u, const float* a1, const float* bias, float* out, int32_t B,
+                             int32_t C, int32_t S, void* stream);
 
 /* fp32 [M,E] -> LayerNorm -> fp16 [M,E] (the GEMM A operand) */
 int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,

@@ -15,7 +15,7 @@ from esm_b200 import pretrained  # noqa: E402
 
 def main():
     B, T = int(os.environ.get("C4_B", 16)), 512
-    model, alphabet = pretrained.load_model_and_alphabet("esm2_t36_3B_UR50D")
+    model, alphabet = pretrained.load_model_and_alphabet("esm2_t36_3B_UR50D", allow_random_init=True)
     model = model.cuda()
     g = torch.Generator().manual_seed(1234)
     tok = torch.randint(4, 24, (B, T), generator=g)

@@ -40,7 +40,7 @@ def main():
            "msa_per_s": round(1e3 / ms, 2), "TFLOP/s": round(flops / ms / 1e9, 1), "finite": bool(torch.isfinite(y).all())}
     # the whole model (embedding prologue, 12 layers, final LayerNorm, LM head) on tokens (1, 128, 512)
     from esm_b200 import pretrained
-    model, _ = pretrained.esm_msa1b_t12_100M_UR50S()
+    model, _ = pretrained.esm_msa1b_t12_100M_UR50S(allow_random_init=True)
     model = model.cuda()
     gt = torch.Generator().manual_seed(1234)
     tokens = torch.randint(4, 24, (1, R, C), generator=gt)   # the 20 standard amino acids, <cls> in column 0, no padding

@@ -26,14 +26,14 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/esmb200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert _lib.load().esmb200_abi_version() == 1
+    assert _lib.load().esmb200_abi_version() == 2
 
 
 def test_workspace_size_is_pure_host_arithmetic():
     from esm_b200 import _lib
     lib = _lib.load()
-    small = lib.esmb200_workspace_bytes(1280, 5120, 1, 1024)
-    big = lib.esmb200_workspace_bytes(1280, 5120, 256, 1024)
+    small = lib.esmb200_workspace_bytes(1280, 20, 5120, 1, 1024)
+    big = lib.esmb200_workspace_bytes(1280, 20, 5120, 256, 1024)
     assert 0 < small < big
     assert big >= 256 * 1024 * (1280 * 2 + 5120 * 2)  # xn + h
 
@@ -57,10 +57,15 @@ def test_no_cpu_fallback():
         model(tokens)
 
 
-def test_head_dim_other_than_64_is_rejected():
+def test_every_esm2_factory_constructs_except_15B():
+    """esm.pretrained.esm2_* (pretrained.py:344-397): head_dim 16 / 24 / 32 / 64 construct (narrow heads run in padded
+    64-wide slots); the 15B model's 128-wide heads are rejected at construction, loudly."""
     from esm_b200 import ESM2
+    for L, E, H in [(1, 320, 20), (1, 480, 20), (1, 640, 20), (1, 1280, 20)]:
+        m = ESM2(num_layers=L, embed_dim=E, attention_heads=H)
+        assert m.layers[0].self_attn.head_dim == E // H
     with pytest.raises(ValueError):
-        ESM2(num_layers=1, embed_dim=320, attention_heads=20)
+        ESM2(num_layers=1, embed_dim=5120, attention_heads=40)
 
 
 def test_state_dict_keys_match_reference_layout():

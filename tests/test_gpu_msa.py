@@ -130,7 +130,7 @@ def test_msa_factory_and_batch_converter_end_to_end():
     """esm_b200.pretrained.esm_msa1b_t12_100M_UR50S() -> (model, alphabet) like the reference's factory; a small MSA
     through the batch converter; contacts [B, C-1, C-1] symmetric in (0, 1)."""
     from esm_b200 import pretrained
-    model, alphabet = pretrained.esm_msa1b_t12_100M_UR50S()
+    model, alphabet = pretrained.esm_msa1b_t12_100M_UR50S(allow_random_init=True)
     model = model.cuda()
     msa = [("s%d" % i, "MKTVRQERLKSIVRILERSKEPVSGAQLAEELSVSRQVIVQDIAYLRSLGYNIVATPRGYVLAGG"[:40]) for i in range(6)]
     _, _, tokens = alphabet.get_batch_converter()(msa)

@@ -62,7 +62,7 @@ def test_checkpoint_upgrade_rule(tmp_path):
 
 
 def test_factories_return_model_and_msa_alphabet():
-    model, alphabet = pretrained.esm_msa1b_t12_100M_UR50S()
+    model, alphabet = pretrained.esm_msa1b_t12_100M_UR50S(allow_random_init=True)
     assert isinstance(model, MSATransformer) and isinstance(alphabet, Alphabet)
     assert (model.args.layers, model.args.embed_dim, model.args.attention_heads) == (12, 768, 12)
     assert model.random_init and alphabet.prepend_bos and not alphabet.append_eos
@@ -78,3 +78,34 @@ def test_no_cpu_fallback_and_argument_checks():
         layer(torch.zeros(2, 8, 1, 128))
     with pytest.raises(ValueError):
         AxialTransformerLayer(100, 256, 2)   # head_dim != 64
+
+
+def test_factories_raise_without_checkpoint_unless_random_init_is_requested(tmp_path):
+    """a missing checkpoint must not silently yield random weights (the reference fails when weights cannot
+    be obtained, pretrained.py:53-64); strict key checking like pretrained.py:200-219."""
+    import warnings
+    from esm_b200 import ESM2
+    with pytest.raises(FileNotFoundError):
+        pretrained.esm2_t33_650M_UR50D()
+    with pytest.raises(FileNotFoundError):
+        pretrained.esm_msa1_t12_100M_UR50S()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model, _ = pretrained.esm2_t6_8M_UR50D(allow_random_init=True)
+    assert model.random_init and any("RANDOM-INIT" in str(x.message) for x in w)
+    # a truncated checkpoint is an error, a checkpoint that only lacks the contact regression loads with a warning
+    from oracle.weights import make_state_dict
+    sd = make_state_dict(2, 128, 2)
+    cfg = {"model": {"encoder_layers": 2, "encoder_embed_dim": 128, "encoder_attention_heads": 2, "token_dropout": True}}
+    full = {("encoder.sentence_encoder." + k): v for k, v in sd.items()}
+    torch.save({"cfg": cfg, "model": {k: v for k, v in full.items() if "layers.1.fc2" not in k}}, tmp_path / "bad.pt")
+    with pytest.raises(RuntimeError, match="Missing key"):
+        pretrained.load_model_and_alphabet(str(tmp_path / "bad.pt"))
+    torch.save({"cfg": cfg, "model": {k: v for k, v in full.items() if "contact_head" not in k}}, tmp_path / "noreg.pt")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model, _ = pretrained.load_model_and_alphabet(str(tmp_path / "noreg.pt"))
+    assert not model.random_init and any("Regression weights not found" in str(x.message) for x in w)
+    torch.save({"cfg": cfg, "model": dict(full, **{"encoder.sentence_encoder.bogus": torch.zeros(1)})}, tmp_path / "extra.pt")
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        pretrained.load_model_and_alphabet(str(tmp_path / "extra.pt"))
