@@ -44,6 +44,10 @@ EXPORTS = (
     "esmb200_profile_enable",
     "esmb200_profile_read",
     "esmb200_set_option",
+    "esmb200_layernorm_split",
+    "esmb200_convert_split",
+    "esmb200_gemm_split",
+    "esmb200_attention_split",
 )
 
 ABI_VERSION = 2
@@ -75,6 +79,7 @@ class LayerWeights(ctypes.Structure):
         ("fc2_weight", c_void_p),
         ("fc2_bias", c_void_p),
         ("head_dim", c_int32),
+        ("precision", c_int32),
     ]
 
 
@@ -95,7 +100,7 @@ def _declare(lib):
     lib.esmb200_layer_destroy.restype = c_int32
     lib.esmb200_layer_destroy.argtypes = [c_void_p]
     lib.esmb200_workspace_bytes.restype = c_size_t
-    lib.esmb200_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32]
+    lib.esmb200_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]
     lib.esmb200_layer_forward.restype = c_int32
     lib.esmb200_layer_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]
@@ -152,6 +157,16 @@ def _declare(lib):
     lib.esmb200_profile_enable.argtypes = [c_int32]
     lib.esmb200_profile_read.restype = c_int32
     lib.esmb200_profile_read.argtypes = [POINTER(c_int32), POINTER(c_float), c_int32]
+    lib.esmb200_layernorm_split.restype = c_int32
+    lib.esmb200_layernorm_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]
+    lib.esmb200_convert_split.restype = c_int32
+    lib.esmb200_convert_split.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
+    lib.esmb200_gemm_split.restype = c_int32
+    lib.esmb200_gemm_split.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.esmb200_attention_split.restype = c_int32
+    lib.esmb200_attention_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                            c_void_p]
     lib.esmb200_set_option.restype = c_int32
     lib.esmb200_set_option.argtypes = [c_char_p, c_int32]
     lib.esmb200_convert_f16.restype = c_int32

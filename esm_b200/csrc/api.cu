@@ -151,6 +151,7 @@ int attn_poly() {
 
 cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& ap, int sms,
                                  cudaStream_t st) {
+  if (ap.lo_off > 0) return launch_attention_v8_poly<0, true>(tq, tkv, ap, sms, st);  // fp32x3: all exponentials on MUFU
   if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
@@ -189,9 +190,22 @@ int check_device() {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
-                cudaStream_t st, int tag = T_GEMM_OTHER) {
+                cudaStream_t st, int tag = T_GEMM_OTHER, bool split = false) {
   ProfScope ps(tag, st);
   cudaError_t e;
+  if (split) {  // fp32x3 precision: operands stored as fp16 hi | lo along K (gemm2.cuh)
+    if (p.K % 64 != 0) return fail(ESMB200_EINVAL, "fp32x3 precision needs K % 64 == 0");
+    switch (epi) {
+      case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE, true>(ta, tb, tout, p, num_sms(), st); break;
+      case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL, true>(ta, tb, tout, p, num_sms(), st); break;
+      case EPI_BIAS_GELU: e = launch_gemm2_epi<EPI_BIAS_GELU, true>(ta, tb, tout, p, num_sms(), st); break;
+      case EPI_BIAS_F32: e = launch_gemm2_epi<EPI_BIAS_F32, true>(ta, tb, tout, p, num_sms(), st); break;
+      case EPI_BIAS_GELU_F32: e = launch_gemm2_epi<EPI_BIAS_GELU_F32, true>(ta, tb, tout, p, num_sms(), st); break;
+      default: return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "gemm launch (fp32x3)");
+    return ESMB200_OK;
+  }
   switch (epi) {
     case EPI_QKV_ROPE: e = launch_gemm2_epi<EPI_QKV_ROPE>(ta, tb, tout, p, num_sms(), st); break;
     case EPI_BIAS_RESIDUAL: e = launch_gemm2_epi<EPI_BIAS_RESIDUAL>(ta, tb, tout, p, num_sms(), st); break;
@@ -251,13 +265,15 @@ int run_key_bits(const uint8_t* pad_mask, const AttnScratch& s, int B, int T, cu
 }
 
 int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batch_stride, int attn_flags,
-                  const AttnScratch& s, int B, int T, int H, cudaStream_t st) {
+                  const AttnScratch& s, int B, int T, int H, cudaStream_t st, bool split = false) {
   const int E = H * 64;
+  const uint64_t qcols = (uint64_t)(split ? 6 : 3) * E;  // fp32x3: [q k v]_hi | [q k v]_lo
   CUtensorMap tq;
-  int rc = make_tmap_f16(&tq, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, 128);
+  int rc = make_tmap_f16(&tq, qkv, (uint64_t)B * T, qcols, qcols, 128);
   if (rc) return rc;
   AttnParams ap;
   ap.B = B; ap.T = T; ap.H = H; ap.E = E;
+  ap.lo_off = split ? 3 * E : 0;
   ap.keybits = s.keybits; ap.kvlen = s.kvlen; ap.words = s.words;
   ap.ctx = static_cast<__half*>(ctx);
   ap.row_max = probs ? s.row_max : nullptr;
@@ -265,7 +281,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
   cudaError_t e;
   {
     CUtensorMap tkv;
-    rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, (uint64_t)3 * E, (uint64_t)3 * E, attn8_cfg::BLOCK_KV);
+    rc = make_tmap_f16(&tkv, qkv, (uint64_t)B * T, qcols, qcols, attn8_cfg::BLOCK_KV);
     if (rc) return rc;
     ProfScope ps(T_ATTN, st);
     e = launch_attention_fwd(tq, tkv, ap, num_sms(), st);
@@ -279,6 +295,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
     pp.row_max = s.row_max; pp.row_sum = s.row_sum; pp.probs = probs;
     pp.batch_stride = probs_batch_stride > 0 ? probs_batch_stride : (long long)H * T * T;
     pp.zero_pad_rows = attn_flags & 1;
+    pp.lo_off = split ? 3 * E : 0;
     {
       ProfScope ps(T_PROBS, st);
       e = launch_attention_probs(tq, pp, st);
@@ -298,6 +315,7 @@ struct esmb200_layer {
   int d;          // head_dim (<= 64); every head occupies a 64-wide slot of the attention-side tensors
   int Ea;         // 64 * H: width of q / k / v / ctx
   float q_scale;  // d^-1/2 (multihead_attention.py:100)
+  int split;      // 1: fp32x3 precision — weights packed as fp16 hi | lo along K, activations likewise
   float eps;
   // borrowed fp32 parameters (owned by the caller, must outlive the layer)
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *out_b, *fc1_b, *fc2_b;
@@ -358,6 +376,17 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   L->q_scale = 1.0f / sqrtf((float)d);
   L->ln1_w = w->ln1_weight; L->ln1_b = w->ln1_bias; L->ln2_w = w->ln2_weight; L->ln2_b = w->ln2_bias;
   L->out_b = w->out_bias; L->fc1_b = w->fc1_bias; L->fc2_b = w->fc2_bias;
+  if (w->precision != 0 && w->precision != 1) {
+    delete L;
+    return fail(ESMB200_EINVAL, "precision must be 0 (fp16 operands) or 1 (fp32x3: fp16 hi|lo operands)");
+  }
+  const int split = w->precision;
+  if (split && (E % 64 != 0 || (has_ffn && F % 64 != 0))) {
+    delete L;
+    return fail(ESMB200_EINVAL, "fp32x3 precision needs embed_dim % 64 == 0 (all ESM-2 models except 35M)");
+  }
+  L->split = split;
+  const size_t pf = split ? 2 : 1;  // fp32x3: every K extent doubles (hi | lo)
   const size_t EaE = (size_t)Ea * E, EF = (size_t)E * F;
   cudaError_t e;
 #define ALLOC(ptr, bytes)                                              \
@@ -365,15 +394,24 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
     esmb200_layer_destroy(L);                                          \
     return fail_cuda(e, "cudaMalloc(packed weights)");                 \
   }
-  ALLOC(L->w_qkv, 3 * EaE * 2);
-  ALLOC(L->w_out, EaE * 2);
+  ALLOC(L->w_qkv, 3 * EaE * 2 * pf);
+  ALLOC(L->w_out, EaE * 2 * pf);
   if (has_ffn) {
-    ALLOC(L->w_fc1, EF * 2);
-    ALLOC(L->w_fc2, EF * 2);
+    ALLOC(L->w_fc1, EF * 2 * pf);
+    ALLOC(L->w_fc2, EF * 2 * pf);
   }
   ALLOC(L->b_qkv, (size_t)3 * Ea * 4);
 #undef ALLOC
-  if (d == 64) {  // slots are full: plain conversion
+  auto convert = [&](const float* src, __half* dst, size_t rows, int K) -> int {  // [rows,K] fp32 -> fp16 (hi | lo)
+    if (!split) return esmb200_convert_f16(src, dst, rows * (size_t)K, stream);
+    size_t blocks = (rows * (size_t)K + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(T_CONVERT, st);
+    convert_f32_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, K);
+    cudaError_t ce = cudaGetLastError();
+    return ce == cudaSuccess ? ESMB200_OK : fail_cuda(ce, "convert_f32_split");
+  };
+  if (d == 64 && !split) {  // slots are full: plain conversion
     rc = esmb200_convert_f16(w->q_weight, L->w_qkv, EaE, stream);
     if (!rc) rc = esmb200_convert_f16(w->k_weight, L->w_qkv + EaE, EaE, stream);
     if (!rc) rc = esmb200_convert_f16(w->v_weight, L->w_qkv + 2 * EaE, EaE, stream);
@@ -384,9 +422,9 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
       if (e == cudaSuccess) e = cudaMemcpyAsync(L->b_qkv + 2 * E, w->v_bias, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) rc = fail_cuda(e, "bias pack");
     }
-  } else {  // head_dim < 64: scatter every head into its zero-padded 64-wide slot
-    e = cudaMemsetAsync(L->w_qkv, 0, 3 * EaE * 2, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(L->w_out, 0, EaE * 2, st);
+  } else {  // head_dim < 64 (scatter every head into its zero-padded 64-wide slot) and / or hi | lo operands
+    e = cudaMemsetAsync(L->w_qkv, 0, 3 * EaE * 2 * pf, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(L->w_out, 0, EaE * 2 * pf, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(L->b_qkv, 0, (size_t)3 * Ea * 4, st);
     if (e != cudaSuccess) rc = fail_cuda(e, "memset(packed weights)");
     const float* ws3[3] = {w->q_weight, w->k_weight, w->v_weight};
@@ -394,22 +432,23 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
     const unsigned blocks = (unsigned)(((size_t)E * E + 255) / 256);
     for (int s3 = 0; s3 < 3 && !rc; ++s3) {
       ProfScope ps(T_CONVERT, st);
-      pack_head_rows_kernel<<<blocks, 256, 0, st>>>(ws3[s3], bs3[s3], L->w_qkv + (size_t)s3 * EaE, L->b_qkv + s3 * Ea, E, d);
+      pack_head_rows_kernel<<<blocks, 256, 0, st>>>(ws3[s3], bs3[s3], L->w_qkv + (size_t)s3 * EaE * pf, L->b_qkv + s3 * Ea,
+                                                    E, d, split);
       if ((e = cudaGetLastError()) != cudaSuccess) rc = fail_cuda(e, "pack_head_rows");
     }
     if (!rc) {
       ProfScope ps(T_CONVERT, st);
-      pack_head_cols_kernel<<<blocks, 256, 0, st>>>(w->out_weight, L->w_out, E, Ea, d);
+      pack_head_cols_kernel<<<blocks, 256, 0, st>>>(w->out_weight, L->w_out, E, Ea, d, split);
       if ((e = cudaGetLastError()) != cudaSuccess) rc = fail_cuda(e, "pack_head_cols");
     }
   }
-  if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc1_weight, L->w_fc1, EF, stream);
-  if (!rc && has_ffn) rc = esmb200_convert_f16(w->fc2_weight, L->w_fc2, EF, stream);
+  if (!rc && has_ffn) rc = convert(w->fc1_weight, L->w_fc1, F, E);
+  if (!rc && has_ffn) rc = convert(w->fc2_weight, L->w_fc2, E, F);
   const uint32_t wbox = gemm2_cfg::HALF_N;
-  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)Ea, E, E, wbox);
-  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, Ea, Ea, wbox);
-  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, E, E, wbox);
-  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, F, F, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_qkv, L->w_qkv, 3 * (uint64_t)Ea, pf * E, pf * E, wbox);
+  if (!rc) rc = make_tmap_f16(&L->tm_out, L->w_out, E, pf * Ea, pf * Ea, wbox);
+  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc1, L->w_fc1, F, pf * E, pf * E, wbox);
+  if (!rc && has_ffn) rc = make_tmap_f16(&L->tm_fc2, L->w_fc2, E, pf * F, pf * F, wbox);
   if (rc) {
     esmb200_layer_destroy(L);
     return rc;
@@ -424,11 +463,11 @@ size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T) {
   return attn_scratch_bytes(B, T, 64);
 }
 
-size_t esmb200_workspace_bytes(int32_t E, int32_t H, int32_t F, int32_t B, int32_t T) {
-  const size_t M = (size_t)B * T, Ea = (size_t)64 * H;
-  const size_t a = align_up(M * E * 2, 1024);                       // xn fp16 [M,E]
-  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2, 1024) + align_up(M * Ea * 2, 1024);
-  const size_t big_h = align_up(M * F * 2, 1024);
+size_t esmb200_workspace_bytes(int32_t E, int32_t H, int32_t F, int32_t B, int32_t T, int32_t precision) {
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * H, pf = precision ? 2 : 1;
+  const size_t a = align_up(M * E * 2 * pf, 1024);                  // xn fp16 [M,E] (hi | lo)
+  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2 * pf, 1024) + align_up(M * Ea * 2 * pf, 1024);
+  const size_t big_h = align_up(M * F * 2 * pf, 1024);
   const size_t big = big_qkv_ctx > big_h ? big_qkv_ctx : big_h;    // h aliases qkv+ctx
   return a + big + attn_scratch_bytes(B, T, H) + 1024;
 }
@@ -442,17 +481,17 @@ struct Workspace {
   AttnScratch as;
 };
 
-int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, int F, int B, int T) {
-  if (bytes < esmb200_workspace_bytes(E, H, F, B, T)) return fail(ESMB200_EWORKSPACE, "workspace too small");
-  const size_t M = (size_t)B * T, Ea = (size_t)64 * H;
+int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, int F, int B, int T, int split) {
+  if (bytes < esmb200_workspace_bytes(E, H, F, B, T, split)) return fail(ESMB200_EWORKSPACE, "workspace too small");
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * H, pf = split ? 2 : 1;
   uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   ws->xn = reinterpret_cast<__half*>(p);
-  p += align_up(M * E * 2, 1024);
+  p += align_up(M * E * 2 * pf, 1024);
   ws->qkv = reinterpret_cast<__half*>(p);
   ws->h = reinterpret_cast<__half*>(p);
-  ws->ctx = reinterpret_cast<__half*>(p + align_up(M * 3 * Ea * 2, 1024));
-  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2, 1024) + align_up(M * Ea * 2, 1024);
-  const size_t big_h = align_up(M * F * 2, 1024);
+  ws->ctx = reinterpret_cast<__half*>(p + align_up(M * 3 * Ea * 2 * pf, 1024));
+  const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2 * pf, 1024) + align_up(M * Ea * 2 * pf, 1024);
+  const size_t big_h = align_up(M * F * 2 * pf, 1024);
   p += big_qkv_ctx > big_h ? big_qkv_ctx : big_h;
   ws->as = carve_attn_scratch(p, B, T, H);
   return ESMB200_OK;
@@ -468,11 +507,13 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
                        const ActMaps& am, cudaStream_t st) {
   const int E = L->E, F = L->F, H = L->H, Ea = L->Ea;
   const int M = B * T;
+  const bool split = L->split != 0;
   cudaError_t e;
   // LN1 -> fp16 (modules.py:124)
   {
     ProfScope ps(T_LN1, st);
-    e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+    e = split ? launch_layernorm<2>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st)
+              : launch_layernorm<1>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "layernorm1");
   // q,k,v projections + bias + q scale + RoPE (multihead_attention.py:258-261,354-355)
@@ -480,40 +521,42 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * Ea; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * Ea;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = Ea; g.q_scale = L->q_scale; g.chunked = 1;
-  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV);
+  g.lo_col_off = 3 * Ea;
+  int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV, split);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
-  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st);
+  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st, split);
   if (rc) return rc;
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = Ea; g.bias = L->out_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT, split);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
   {
     ProfScope ps(T_LN2, st);
-    e = launch_layernorm<true>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
+    e = split ? launch_layernorm<2>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st)
+              : launch_layernorm<1>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "layernorm2");
   // fc1 + GELU (modules.py:138)
   memset(&g, 0, sizeof g);
-  g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F;
-  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.h, g, st, T_FC1);
+  g.M = M; g.N = F; g.K = E; g.bias = L->fc1_b; g.out = ws.h; g.ldo = F; g.lo_col_off = F;
+  rc = launch_gemm(EPI_BIAS_GELU, am.xn, L->tm_fc1, am.h, g, st, T_FC1, split);
   if (rc) return rc;
   // fc2 + residual (modules.py:139-140)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2);
+  rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2, split);
   return rc;
 }
 
-int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int H, int F, int M) {
-  const uint64_t Ea = (uint64_t)64 * H;
-  int rc = make_tmap_f16(&am->xn, ws.xn, M, E, E, gemm2_cfg::BOX_M);
-  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, Ea, Ea, gemm2_cfg::BOX_M);
-  if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, F, F, gemm2_cfg::BOX_M);
-  if (!rc) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, 3 * Ea, 3 * Ea, 128);
+int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int H, int F, int M, int split = 0) {
+  const uint64_t Ea = (uint64_t)64 * H, pf = split ? 2 : 1;  // fp32x3: every fp16 activation is [rows, 2 * width]
+  int rc = make_tmap_f16(&am->xn, ws.xn, M, pf * E, pf * E, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, pf * Ea, pf * Ea, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, pf * F, pf * F, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&am->qkv_out, ws.qkv, M, pf * 3 * Ea, pf * 3 * Ea, 128);
   if (!rc) rc = make_tmap_2d(&am->x_out, x, 4, M, E, E, 128);
   return rc;
 }
@@ -533,13 +576,14 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   const int E = layers[0]->E, F = layers[0]->F, H = layers[0]->H;
   if (F <= 0) return fail(ESMB200_EINVAL, "attention-only layers belong to esmb200_axial_stack_forward");
   for (int i = 1; i < n_layers; ++i)
-    if (layers[i]->E != E || layers[i]->F != F || layers[i]->H != H)
-      return fail(ESMB200_EINVAL, "layers of one stack must share E, H and F");
+    if (layers[i]->E != E || layers[i]->F != F || layers[i]->H != H || layers[i]->split != layers[0]->split)
+      return fail(ESMB200_EINVAL, "layers of one stack must share E, H, F and precision");
+  const int split = layers[0]->split;
   Workspace ws;
-  rc = carve_workspace(&ws, workspace, workspace_bytes, E, H, F, B, T);
+  rc = carve_workspace(&ws, workspace, workspace_bytes, E, H, F, B, T, split);
   if (rc) return rc;
   ActMaps am;
-  rc = make_act_maps(&am, ws, x, E, H, F, B * T);
+  rc = make_act_maps(&am, ws, x, E, H, F, B * T, split);
   if (rc) return rc;
   rc = run_key_bits(pad_mask, ws.as, B, T, st);
   if (rc) return rc;
@@ -578,7 +622,7 @@ int esmb200_layernorm(const float* x, const float* weight, const float* bias, fl
                       float eps, void* stream) {
   if (!x || !weight || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
   ProfScope ps(T_LN_F32, static_cast<cudaStream_t>(stream));
-  cudaError_t e = launch_layernorm<false>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_layernorm<0>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "layernorm");
   return ESMB200_OK;
 }
@@ -587,7 +631,7 @@ int esmb200_layernorm_f16(const float* x, const float* weight, const float* bias
                           float eps, void* stream) {
   if (!x || !weight || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
   ProfScope ps(T_LN1, static_cast<cudaStream_t>(stream));
-  cudaError_t e = launch_layernorm<true>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_layernorm<1>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail_cuda(e, "layernorm_f16");
   return ESMB200_OK;
 }
@@ -615,6 +659,66 @@ int esmb200_gemm_f16(int32_t epilogue, const void* a, const void* w, const float
   g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = N;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
   return launch_gemm(epilogue, ta, tb, tout, g, static_cast<cudaStream_t>(stream));
+}
+
+// ---- fp32x3 precision building blocks (hi | lo fp16 operands): used by the LM head and the kernel-level parity tests
+int esmb200_layernorm_split(const float* x, const float* weight, const float* bias, void* out, int32_t M, int32_t E,
+                            float eps, void* stream) {
+  if (!x || !weight || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
+  ProfScope ps(T_LN1, static_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_layernorm<2>(x, weight, bias, out, M, E, eps, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(e, "layernorm_split");
+  return ESMB200_OK;
+}
+
+int esmb200_convert_split(const float* src, void* dst, int64_t rows, int32_t K, void* stream) {
+  if (!src || !dst) return fail(ESMB200_EINVAL, "null argument");
+  if (rows <= 0 || K <= 0) return ESMB200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t blocks = ((size_t)rows * K + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps(T_CONVERT, st);
+  convert_f32_split_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, static_cast<__half*>(dst), (size_t)rows, K);
+  CK(cudaGetLastError());
+  return ESMB200_OK;
+}
+
+int esmb200_gemm_split(int32_t epilogue, const void* a, const void* w, const float* bias, void* out, int32_t M,
+                       int32_t N, int32_t K, const float* rope_cos, const float* rope_sin, int32_t T, int32_t E,
+                       void* stream) {
+  if (!a || !w || !bias || !out) return fail(ESMB200_EINVAL, "null argument");
+  const bool f16_out = (epilogue == EPI_QKV_ROPE || epilogue == EPI_BIAS_GELU);
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % (f16_out ? 64 : 32) != 0)
+    return fail(ESMB200_EINVAL, "split gemm needs K % 64 == 0 and N % 64 == 0 (fp16 output) / N % 32 == 0 (fp32 output)");
+  if (epilogue < 0 || epilogue > EPI_BIAS_GELU_F32) return fail(ESMB200_EINVAL, "unknown GEMM epilogue");
+  int rc = check_device();
+  if (rc) return rc;
+  if (epilogue == EPI_QKV_ROPE && (!rope_cos || !rope_sin || T <= 0 || E <= 0 || E % 64 != 0 || N != 3 * E))
+    return fail(ESMB200_EINVAL, "qkv epilogue needs rope tables, T and N == 3E");
+  CUtensorMap ta, tb, tout;
+  rc = make_tmap_f16(&ta, a, M, 2 * (uint64_t)K, 2 * (uint64_t)K, gemm2_cfg::BOX_M);
+  if (!rc) rc = make_tmap_f16(&tb, w, N, 2 * (uint64_t)K, 2 * (uint64_t)K, gemm2_cfg::HALF_N);
+  if (!rc) rc = f16_out ? make_tmap_2d(&tout, out, 2, M, 2 * (uint64_t)N, 2 * (uint64_t)N, 128)
+                        : make_tmap_2d(&tout, out, 4, M, N, N, 128);
+  if (rc) return rc;
+  GemmParams g;
+  memset(&g, 0, sizeof g);
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = N; g.lo_col_off = N;
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = E; g.q_scale = 0.125f;
+  return launch_gemm(epilogue, ta, tb, tout, g, static_cast<cudaStream_t>(stream), T_GEMM_OTHER, true);
+}
+
+int esmb200_attention_split(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,
+                            int32_t H, void* scratch, void* stream) {
+  if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || T <= 0 || H <= 0 || H > 64) return fail(ESMB200_EINVAL, "bad shape");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnScratch s = carve_attn_scratch(scratch, B, T, H);
+  rc = run_key_bits(pad_mask, s, B, T, st);
+  if (rc) return rc;
+  return run_attention(qkv, ctx, attn_probs, 0, 0, s, B, T, H, st, true);
 }
 
 int esmb200_gemm_qkv_f16(const void* a, const void* w, const float* bias, void* out, int32_t M, int32_t E, float q_scale,
@@ -743,7 +847,7 @@ int esmb200_column_attention(const void* qkv, const uint8_t* pad_mask, void* ctx
 
 
 size_t esmb200_axial_workspace_bytes(int32_t E, int32_t F, int32_t B, int32_t R, int32_t C) {
-  return esmb200_workspace_bytes(E, E / 64, F, B * C, R) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
+  return esmb200_workspace_bytes(E, E / 64, F, B * C, R, 0) + esmb200_tied_row_attention_scratch_bytes(B, C, E / 64) + 1024;
 }
 
 // (A CUDA-graph replay of this launch sequence was measured: 20.70 vs 20.77 ms per 128 x 512 MSA — the ~2 ms between the
@@ -770,8 +874,11 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
   const int M = B * R * C;
   Workspace ws;
   if (E != 64 * H) return fail(ESMB200_EINVAL, "the MSA axial path needs head_dim 64");
-  const size_t base_bytes = esmb200_workspace_bytes(E, H, F, B * C, R);
-  rc = carve_workspace(&ws, workspace, base_bytes, E, H, F, B * C, R);
+  for (int i = 0; i < n_layers; ++i)
+    if (row_layers[i]->split || col_layers[i]->split)
+      return fail(ESMB200_EINVAL, "the MSA axial path runs with fp16 operands only (precision 0)");
+  const size_t base_bytes = esmb200_workspace_bytes(E, H, F, B * C, R, 0);
+  rc = carve_workspace(&ws, workspace, base_bytes, E, H, F, B * C, R, 0);
   if (rc) return rc;
   uint8_t* tied_scratch = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024)) + base_bytes;
   const size_t tied_bytes = esmb200_tied_row_attention_scratch_bytes(B, C, H);
@@ -792,7 +899,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     esmb200_layer* L = row_layers[i];
     {
       ProfScope ps(T_LN1, st);
-      e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+      e = launch_layernorm<1>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "row layernorm");
     memset(&g, 0, sizeof g);
@@ -816,7 +923,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     L = col_layers[i];
     {
       ProfScope ps(T_LN1, st);
-      e = launch_layernorm<true>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
+      e = launch_layernorm<1>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "column layernorm");
     memset(&g, 0, sizeof g);
@@ -840,7 +947,7 @@ int esmb200_axial_stack_forward(esmb200_layer* const* row_layers, esmb200_layer*
     // ---------------- feed-forward (modules.py:213-214, 413-418) ----------------
     {
       ProfScope ps(T_LN2, st);
-      e = launch_layernorm<true>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
+      e = launch_layernorm<1>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "ffn layernorm");
     memset(&g, 0, sizeof g);

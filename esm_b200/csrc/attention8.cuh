@@ -40,6 +40,10 @@ constexpr int NUM_THREADS = 192;       // warp 0 TMA, warp 1 MMA issuer + TMEM o
 constexpr int CTAS_PER_SM = 4;
 constexpr int TMEM_COLS = 128;
 constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 1024 + 128;
+// SPLIT ("fp32x3" precision): q, k, v and P are fp16 hi | lo pairs, every product runs hi*hi + lo*hi + hi*lo into the
+// same fp32 accumulator.  Twice the shared memory per tile -> 2 CTAs per SM.
+constexpr int SMEM_BYTES_SPLIT = 2 * Q_BYTES + KV_STAGES * 4 * KV_BYTES + 1024 + 128;
+constexpr int CTAS_PER_SM_SPLIT = 2;
 constexpr float SUM_LIMIT = 4096.0f;   // raise the reference when a block's row sum exceeds this
 }  // namespace attn8_cfg
 
@@ -78,18 +82,21 @@ __device__ __forceinline__ void attn8_exp_half(const uint32_t (&sv)[32], uint32_
   }
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, attn8_cfg::CTAS_PER_SM)
+template <int POLY, bool SPLIT = false>
+__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, SPLIT ? attn8_cfg::CTAS_PER_SM_SPLIT : attn8_cfg::CTAS_PER_SM)
 attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                         const AttnParams p) {
   using namespace attn8_cfg;
   constexpr float LOG2E = attn_cfg::LOG2E;
+  constexpr int NP = SPLIT ? 2 : 1;            // operand parts: hi (+ lo)
+  constexpr int QB = NP * Q_BYTES;             // Q tile(s) of one work item
+  constexpr int KB = NP * KV_BYTES;            // K tile(s) / V tile(s) of one stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem + Q_BYTES;                         // KV_STAGES buffers
-  uint8_t* smem_v = smem + Q_BYTES + KV_STAGES * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + KV_STAGES * 2 * KV_BYTES);
+  uint8_t* smem_q = smem;                                   // [hi | lo]
+  uint8_t* smem_k = smem + QB;                              // KV_STAGES x [hi | lo]
+  uint8_t* smem_v = smem + QB + KV_STAGES * KB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QB + KV_STAGES * 2 * KB);
   uint64_t* q_full = bars;         // [1] TMA -> MMA
   uint64_t* q_empty = bars + 1;    // [1] MMA -> TMA (every QK^T of the tile has completed)
   uint64_t* kv_full = bars + 2;    // [2] TMA -> MMA
@@ -148,14 +155,21 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int row_base = (b / p.cols) * p.T;
         const int x0 = (b % p.cols) * 3 * p.E + h * HEAD_DIM;
         mbar_wait_relaxed(q_empty, (tq & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, Q_BYTES);
-        tma_load_2d(smem_q, &tmap_q, q_full, x0, row_base + qt * BLOCK_Q);
+        mbar_arrive_expect_tx(q_full, QB);
+#pragma unroll
+        for (int part = 0; part < NP; ++part)
+          tma_load_2d(smem_q + part * Q_BYTES, &tmap_q, q_full, x0 + part * p.lo_off, row_base + qt * BLOCK_Q);
         for (int i = 0; i < nblk; ++i, ++g) {
           const uint32_t s = g % KV_STAGES;
           mbar_wait_relaxed(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
-          tma_load_2d(smem_k + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E, row_base + i * BLOCK_KV);
-          tma_load_2d(smem_v + s * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E, row_base + i * BLOCK_KV);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * KB);
+#pragma unroll
+          for (int part = 0; part < NP; ++part) {
+            tma_load_2d(smem_k + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E + part * p.lo_off,
+                        row_base + i * BLOCK_KV);
+            tma_load_2d(smem_v + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E + part * p.lo_off,
+                        row_base + i * BLOCK_KV);
+          }
         }
         ++tq;
       }
@@ -166,14 +180,22 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 64, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, true);
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q), 1024, 0);
+      const uint64_t qdesc_lo = umma_smem_desc_sw128(smem_u32(smem_q + Q_BYTES), 1024, 0);  // SPLIT only
       uint32_t g = 0, tq = 0, np = 0;
       auto issue_qk = [&](uint32_t gg, bool last) {
         const uint32_t s = gg % KV_STAGES;
         mbar_wait(&kv_full[s], (gg / KV_STAGES) & 1);
         tc_fence_after();
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * KV_BYTES), 1024, 0);
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * KB), 1024, 0);
 #pragma unroll
         for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        if constexpr (SPLIT) {  // + q_lo k_hi + q_hi k_lo
+          const uint64_t kdesc_lo = umma_smem_desc_sw128(smem_u32(smem_k + s * KB + KV_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc_lo + 2 * k, kdesc + 2 * k, idesc_qk, 1u);
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc_lo + 2 * k, idesc_qk, 1u);
+        }
         tc_commit(s_full);
         tc_commit(&kv_empty[s]);
         if (last) tc_commit(q_empty);  // every QK^T of this tile has been issued: Q may be reloaded when they finish
@@ -187,10 +209,17 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const uint32_t s = g % KV_STAGES;
           mbar_wait(p_full, np & 1);  // P_j stored (and, on the first block of a tile, the previous O read out)
           tc_fence_after();
-          const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KV_BYTES), 1024, 8192);
+          const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KB), 1024, 8192);
 #pragma unroll
           for (int k = 0; k < BLOCK_KV / 16; ++k)
             umma_ts(tmem_o, tmem_s + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          if constexpr (SPLIT) {  // + p_lo v_hi + p_hi v_lo (P_lo lives in columns [32,64) of the S buffer)
+            const uint64_t vdesc_lo = umma_smem_desc_sw128(smem_u32(smem_v + s * KB + KV_BYTES), 1024, 8192);
+#pragma unroll
+            for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(tmem_o, tmem_s + 32 + 8 * k, vdesc + 128 * k, idesc_pv, 1u);
+#pragma unroll
+            for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(tmem_o, tmem_s + 8 * k, vdesc_lo + 128 * k, idesc_pv, 1u);
+          }
           tc_commit(&kv_empty[s]);
 #ifdef ESMB200_ATTN8_SAFE_WAR
           tc_commit(pv_done);
@@ -245,6 +274,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
         float rsum = 0.f;
         uint32_t pk[2][16];
+        [[maybe_unused]] uint32_t pl[2][16];  // SPLIT: the lo halves of P
         for (int trip = 0;; ++trip) {
           const float mneg = -m_ref * LOG2E;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -253,7 +283,22 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
             uint32_t sv[32];
             tmem_ld_32x32b_x32(ts + c * 32, sv);
             tmem_wait_ld_dep(sv);
-            attn8_exp_half<POLY>(sv, kw[c], mneg, sum, pk[c]);
+            if constexpr (SPLIT) {
+              const uint32_t wd = kw[c];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool k0 = (wd >> (2 * i)) & 1u, k1 = (wd >> (2 * i + 1)) & 1u;
+                const float p0 = k0 ? ex2_approx(fmaf(__uint_as_float(sv[2 * i]), LOG2E, mneg)) : 0.f;
+                const float p1 = k1 ? ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), LOG2E, mneg)) : 0.f;
+                sum[i & 3] += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                const float2 f = __half22float2(h2);
+                pk[c][i] = *reinterpret_cast<const uint32_t*>(&h2);
+                pl[c][i] = pack_half2(p0 - f.x, p1 - f.y);
+              }
+            } else {
+              attn8_exp_half<POLY>(sv, kw[c], mneg, sum, pk[c]);
+            }
           }
           rsum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
           if (trip == 1) break;
@@ -292,6 +337,10 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         // P_j over the first 32 columns of S_j (this thread's own row, already consumed)
         tmem_st_32x32b_x16(ts, pk[0]);
         tmem_st_32x32b_x16(ts + 16, pk[1]);
+        if constexpr (SPLIT) {
+          tmem_st_32x32b_x16(ts + 32, pl[0]);
+          tmem_st_32x32b_x16(ts + 48, pl[1]);
+        }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(p_full);
@@ -300,6 +349,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
       // ---- tile epilogue: O / l -> ctx
       uint32_t outv[32];
+      [[maybe_unused]] uint32_t outl[32];  // SPLIT: lo halves of the context
       if (nblk > 0) {
         mbar_wait(o_full, nt & 1);
         ++nt;
@@ -311,13 +361,23 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_ld_32x32b_x32(tmem_o + lane_addr + hlf * 32, ov);
           tmem_wait_ld_dep(ov);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            outv[hlf * 16 + i] = pack_half2(__uint_as_float(ov[2 * i]) * inv, __uint_as_float(ov[2 * i + 1]) * inv);
+          for (int i = 0; i < 16; ++i) {
+            const float y0 = __uint_as_float(ov[2 * i]) * inv, y1 = __uint_as_float(ov[2 * i + 1]) * inv;
+            const __half2 h2 = __floats2half2_rn(y0, y1);
+            outv[hlf * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
+            if constexpr (SPLIT) {
+              const float2 f = __half22float2(h2);
+              outl[hlf * 16 + i] = pack_half2(y0 - f.x, y1 - f.y);
+            }
+          }
         }
         tc_fence_before();
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) outv[i] = 0u;
+        for (int i = 0; i < 32; ++i) {
+          outv[i] = 0u;
+          if constexpr (SPLIT) outl[i] = 0u;
+        }
       }
       if (t < p.T) {
         if (p.row_max != nullptr) {
@@ -325,9 +385,15 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
           p.row_max[si] = m_ref;
           p.row_sum[si] = l_run;
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * p.E + h * HEAD_DIM);
+        const size_t pitch = SPLIT ? 2 * (size_t)p.E : (size_t)p.E;  // SPLIT: ctx [M, 2E] = hi | lo
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * pitch + h * HEAD_DIM);
 #pragma unroll
         for (int v = 0; v < 8; ++v) dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
+        if constexpr (SPLIT) {
+          uint4* dl = dst + p.E / 8;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) dl[v] = make_uint4(outl[4 * v], outl[4 * v + 1], outl[4 * v + 2], outl[4 * v + 3]);
+        }
       }
     }
   }
@@ -340,17 +406,18 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-template <int POLY>
+template <int POLY, bool SPLIT = false>
 inline cudaError_t launch_attention_v8_poly(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const AttnParams& p,
                                             int num_sms, cudaStream_t stream) {
   using namespace attn8_cfg;
-  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES);
+  constexpr int smem = SPLIT ? SMEM_BYTES_SPLIT : SMEM_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem);
   if (e != cudaSuccess) return e;
   const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
-  const long long cap = (long long)CTAS_PER_SM * num_sms;
+  const long long cap = (long long)(SPLIT ? CTAS_PER_SM_SPLIT : CTAS_PER_SM) * num_sms;
   const int grid = (int)(total < cap ? total : cap);
-  return launch_pdl(attention_fwd_kernel_v8<POLY>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_q, tmap_kv, p);
+  return launch_pdl(attention_fwd_kernel_v8<POLY, SPLIT>, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, p);
 }
 
 }  // namespace esmb200

@@ -18,6 +18,7 @@ struct AttnParams {
   __half* ctx;              // [B*T, E] attention output, heads merged (column h*64 + j)
   float* row_max;           // optional [B,H,T]: final softmax row max (of the scaled scores) ...
   float* row_sum;           // optional [B,H,T]: ... and row sum of exp(s - max), for attention_probs_kernel
+  int lo_off = 0;           // fp32x3 precision: column offset (elements) of the lo halves in qkv [M, 6E] (= 3E)
   int cols = 1;             // sequence s = (s / cols, s % cols) of a [B/cols, T, cols, 3E] tensor
                             // (MSA column attention: the T tokens of a sequence are `cols` rows apart)
 };

@@ -20,24 +20,28 @@ struct ProbsParams {
   float* probs;  // [B,H,T,T], batch b starting at probs + b * batch_stride (elements)
   long long batch_stride;
   int zero_pad_rows;  // 1: rows of padded query tokens are written as zeros (ESM2.forward's stacked result)
+  int lo_off;         // fp32x3 precision: column offset of the lo halves in qkv [M, 6E] (0 = plain fp16 operands)
 };
 
 namespace probs_cfg {
 constexpr int NUM_THREADS = 128;
 constexpr int TMEM_COLS = 128;
 constexpr int BLOCK_Q = 128, BLOCK_KV = 128;
+constexpr int SMEM_BYTES_SPLIT = 4 * attn_cfg::TILE_BYTES + 1024 + 64 + 4 * 32 * 33 * 4;  // fp32x3: Q, K as hi | lo
 constexpr int SMEM_BYTES = 2 * attn_cfg::TILE_BYTES + 1024 + 64 + 4 * 32 * 33 * 4;  // + per-warp transpose tiles
 }  // namespace probs_cfg
 
-__global__ void __launch_bounds__(probs_cfg::NUM_THREADS, 4)
+template <bool SPLIT>
+__global__ void __launch_bounds__(probs_cfg::NUM_THREADS, SPLIT ? 2 : 4)
 attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const ProbsParams p) {
   using namespace attn_cfg;
   using namespace probs_cfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem + TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * TILE_BYTES);
+  constexpr int NP = SPLIT ? 2 : 1;
+  uint8_t* smem_q = smem;                    // [hi | lo]
+  uint8_t* smem_k = smem + NP * TILE_BYTES;  // [hi | lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * NP * TILE_BYTES);
   uint64_t* ld_full = bars;
   uint64_t* mma_done = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -66,9 +70,12 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
   const bool live = k0 < p.kvlen[b];  // otherwise every key of this block is masked: probabilities are exactly 0
 
   if (live && threadIdx.x == 0) {
-    mbar_arrive_expect_tx(ld_full, 2 * TILE_BYTES);
-    tma_load_2d(smem_q, &tmap_qkv, ld_full, h * HEAD_DIM, row_base + q0);
-    tma_load_2d(smem_k, &tmap_qkv, ld_full, p.E + h * HEAD_DIM, row_base + k0);
+    mbar_arrive_expect_tx(ld_full, 2 * NP * TILE_BYTES);
+#pragma unroll
+    for (int part = 0; part < NP; ++part) {
+      tma_load_2d(smem_q + part * TILE_BYTES, &tmap_qkv, ld_full, h * HEAD_DIM + part * p.lo_off, row_base + q0);
+      tma_load_2d(smem_k + part * TILE_BYTES, &tmap_qkv, ld_full, p.E + h * HEAD_DIM + part * p.lo_off, row_base + k0);
+    }
     mbar_wait(ld_full, 0);
     tc_fence_after();
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, false);
@@ -76,6 +83,14 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
     const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k), 1024, 0);
 #pragma unroll
     for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+    if constexpr (SPLIT) {
+      const uint64_t qlo = umma_smem_desc_sw128(smem_u32(smem_q + TILE_BYTES), 1024, 0);
+      const uint64_t klo = umma_smem_desc_sw128(smem_u32(smem_k + TILE_BYTES), 1024, 0);
+#pragma unroll
+      for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qlo + 2 * k, kdesc + 2 * k, idesc_qk, 1u);
+#pragma unroll
+      for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, klo + 2 * k, idesc_qk, 1u);
+    }
     tc_commit(mma_done);
   }
   __syncwarp();
@@ -87,7 +102,7 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
   const int t = t_warp0 + lane;
   const bool row_ok = t < p.T;
   const int ncols = min(BLOCK_KV, p.T - k0);
-  float* tile = reinterpret_cast<float*>(smem + 2 * TILE_BYTES + 64) + warp * (32 * 33);
+  float* tile = reinterpret_cast<float*>(smem + 2 * NP * TILE_BYTES + 64) + warp * (32 * 33);
   float* base = p.probs + (size_t)b * p.batch_stride + (size_t)h * p.T * p.T + k0;
   float mneg = 0.f, inv = 0.f;
   uint32_t kw[4] = {0u, 0u, 0u, 0u};
@@ -137,10 +152,17 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
 
 inline cudaError_t launch_attention_probs(const CUtensorMap& tmap_qkv, const ProbsParams& p, cudaStream_t stream) {
   using namespace probs_cfg;
-  cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return e;
   dim3 grid((p.T + BLOCK_KV - 1) / BLOCK_KV, (p.T + BLOCK_Q - 1) / BLOCK_Q, p.B * p.H);
-  return launch_pdl(attention_probs_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_qkv, p);
+  if (p.lo_off > 0) {
+    cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES_SPLIT);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(attention_probs_kernel<true>, grid, dim3(NUM_THREADS), SMEM_BYTES_SPLIT, stream, tmap_qkv, p);
+  }
+  cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(attention_probs_kernel<false>, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_qkv, p);
 }
 
 }  // namespace esmb200

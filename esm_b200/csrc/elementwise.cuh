@@ -14,7 +14,9 @@
 namespace esmb200 {
 
 // Each lane owns float4 chunks lane, lane+32, ... of the row. MAXV bounds E <= MAXV*128.
-template <int MAXV, bool OUT_HALF>
+// OUT: 0 = fp32 [M,E]; 1 = fp16 [M,E] (GEMM A operand); 2 = fp16 hi | lo [M,2E] (A operand of the fp32x3 GEMMs:
+// hi = rn(y) in columns [0,E), lo = rn(y - hi) in columns [E,2E)).
+template <int MAXV, int OUT>
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta, void* out, int M,
                       int E, float eps) {  // x and out may alias (in-place final LayerNorm): a warp reads its whole row first
@@ -59,11 +61,22 @@ layernorm_rows_kernel(const float* x, const float* __restrict__ gamma, const flo
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if constexpr (OUT_HALF) {
+      if constexpr (OUT == 1) {
         uint2 h;
         h.x = pack_half2(o.x, o.y);
         h.y = pack_half2(o.z, o.w);
         reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (size_t)row * E)[idx] = h;
+      } else if constexpr (OUT == 2) {
+        const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        uint2 h, l;
+        h.x = *reinterpret_cast<const uint32_t*>(&h01);
+        h.y = *reinterpret_cast<const uint32_t*>(&h23);
+        l.x = pack_half2(o.x - f01.x, o.y - f01.y);
+        l.y = pack_half2(o.z - f23.x, o.w - f23.y);
+        __half* orow = reinterpret_cast<__half*>(out) + (size_t)row * 2 * E;
+        reinterpret_cast<uint2*>(orow)[idx] = h;
+        reinterpret_cast<uint2*>(orow + E)[idx] = l;
       } else {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * E)[idx] = o;
       }
@@ -71,7 +84,7 @@ layernorm_rows_kernel(const float* x, const float* __restrict__ gamma, const flo
   }
 }
 
-template <bool OUT_HALF>
+template <int OUT>
 inline cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int E,
                                     float eps, cudaStream_t stream) {
   if (E % 4 != 0 || E > 40 * 128) return cudaErrorInvalidValue;
@@ -79,10 +92,10 @@ inline cudaError_t launch_layernorm(const float* x, const float* gamma, const fl
   const int grid = (M + wpb - 1) / wpb;
   if (grid == 0) return cudaSuccess;
   const dim3 g(grid), b(wpb * 32);
-  if (E <= 4 * 128) return launch_pdl(layernorm_rows_kernel<4, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
-  if (E <= 10 * 128) return launch_pdl(layernorm_rows_kernel<10, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
-  if (E <= 20 * 128) return launch_pdl(layernorm_rows_kernel<20, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
-  return launch_pdl(layernorm_rows_kernel<40, OUT_HALF>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  if (E <= 4 * 128) return launch_pdl(layernorm_rows_kernel<4, OUT>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  if (E <= 10 * 128) return launch_pdl(layernorm_rows_kernel<10, OUT>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  if (E <= 20 * 128) return launch_pdl(layernorm_rows_kernel<20, OUT>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
+  return launch_pdl(layernorm_rows_kernel<40, OUT>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
 }
 
 // One block per sequence: counts <mask>/<pad>, then writes the scaled embedding rows.
@@ -174,6 +187,19 @@ __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __
   for (; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
 }
 
+// fp32x3 operands: src [rows, K] fp32 -> dst [rows, 2K] fp16, hi = rn(x) in columns [0,K), lo = rn(x - hi) in [K,2K)
+__global__ void convert_f32_split_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t rows, int K) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = rows * (size_t)K, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const size_t r = i / K, k = i % K;
+    const float x = src[i];
+    const __half h = __float2half_rn(x);
+    dst[r * 2 * K + k] = h;
+    dst[r * 2 * K + K + k] = __float2half_rn(x - __half2float(h));
+  }
+}
+
 // head_dim < 64: every head's projection rows go to a zero-padded 64-wide slot, first half of the head at slot
 // positions [0, d/2), second half at [32, 32 + d/2) so that the RoPE epilogue's (j, j+32) pairing reproduces the
 // reference's (j, j+d/2) rotate-half pairs (rotary_embedding.py:11-20).  dst must be zero-filled by the caller.
@@ -181,20 +207,28 @@ __device__ __forceinline__ int head_slot(int n, int d) {  // projection output i
   const int h = n / d, j = n % d;
   return h * 64 + (j < d / 2 ? j : 32 + (j - d / 2));
 }
+// split != 0: fp32x3 operand layout, row pitch 2K with the lo halves K columns to the right
 __global__ void pack_head_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ dst,
-                                      float* __restrict__ bdst, int E, int d) {  // w [E,E] -> dst [64*H, E]
+                                      float* __restrict__ bdst, int E, int d, int split) {  // w [E,E] -> dst [64*H, E]
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)E * E) return;
   const int n = (int)(i / E), k = (int)(i % E);
   const int r = head_slot(n, d);
-  dst[(size_t)r * E + k] = __float2half_rn(w[i]);
+  const __half h = __float2half_rn(w[i]);
+  const size_t pitch = split ? 2 * (size_t)E : (size_t)E;
+  dst[(size_t)r * pitch + k] = h;
+  if (split) dst[(size_t)r * pitch + E + k] = __float2half_rn(w[i] - __half2float(h));
   if (k == 0) bdst[r] = b[n];
 }
-__global__ void pack_head_cols_kernel(const float* __restrict__ w, __half* __restrict__ dst, int E, int Ea, int d) {
+__global__ void pack_head_cols_kernel(const float* __restrict__ w, __half* __restrict__ dst, int E, int Ea, int d,
+                                      int split) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // w [E,E] (out_proj) -> dst [E, Ea]
   if (i >= (size_t)E * E) return;
   const int n = (int)(i / E), k = (int)(i % E);
-  dst[(size_t)n * Ea + head_slot(k, d)] = __float2half_rn(w[i]);
+  const __half h = __float2half_rn(w[i]);
+  const size_t pitch = split ? 2 * (size_t)Ea : (size_t)Ea;
+  dst[(size_t)n * pitch + head_slot(k, d)] = h;
+  if (split) dst[(size_t)n * pitch + Ea + head_slot(k, d)] = __float2half_rn(w[i] - __half2float(h));
 }
 
 // MSA row attention: q is zeroed at padded positions before the logits are summed over the alignment rows

@@ -52,7 +52,11 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
 
 // (a variant writing fp16 rows straight from registers to global memory, without smem staging, measured slower:
 // profiles/r01_epilogue_experiments.txt)
-template <int EPI>
+// SPLIT ("fp32x3" precision): both operands are stored as fp16 hi | lo halves along K (A [M,2K], B [N,2K]); the K loop
+// runs hi*hi + lo*hi + hi*lo (three passes over the same fp32 accumulator: 22 significand bits per operand, the
+// dropped lo*lo term is 2^-22 relative), and fp16 outputs are written as hi | lo pairs as well (lo part p.lo_col_off
+// columns to the right).  Requires K % 64 == 0.
+template <int EPI, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_cfg::NUM_THREADS, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -79,7 +83,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tiles_m = (p.M + PAIR_M - 1) / PAIR_M;
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;  // a partial last K slab is zero-filled by TMA on both operands
+  const int num_kb1 = (p.K + BLOCK_K - 1) / BLOCK_K;  // a partial last K slab is zero-filled by TMA on both operands
+  const int num_kb = SPLIT ? 3 * num_kb1 : num_kb1;   // SPLIT: slab kb/3, operand halves by kb%3
   // Tile walk of this cluster (tile = m_blk * tiles_n + n_blk).  Default: strided — at any moment the clusters cover a few
   // adjacent 256-row slabs of A and all of B, which keeps a long-K A slab (fc2: 2.6 MB) L2-resident while it is reused.
   // p.chunked: one contiguous run per cluster, so consecutive tiles share their rows (the RoPE epilogue then reloads
@@ -133,8 +138,14 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int b_row = n_blk * BLOCK_N + rank * HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
-          tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BLOCK_K, a_row);
-          tma_load_2d_pair(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row);
+          int a_col = kb * BLOCK_K, b_col = kb * BLOCK_K;
+          if constexpr (SPLIT) {
+            const int part = kb % 3;  // 0: hi*hi, 1: lo*hi, 2: hi*lo
+            a_col = (kb / 3) * BLOCK_K + (part == 1 ? p.K : 0);
+            b_col = (kb / 3) * BLOCK_K + (part == 2 ? p.K : 0);
+          }
+          tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], a_col, a_row);
+          tma_load_2d_pair(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], b_col, b_row);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           else mbar_arrive_remote(&full_bar[stage], 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -205,7 +216,82 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N + chalf * 128;
       const int col0 = n_blk * BLOCK_N + chalf * 128;
 
-      if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_GELU_MATHONLY || EPI == EPI_F16_STOREONLY ||
+      if constexpr (SPLIT && (EPI == EPI_BIAS_GELU || EPI == EPI_QKV_ROPE)) {
+        // fp32x3 precision: the fp32 result y of every element is written as fp16 hi = rn(y) and lo = rn(y - hi)
+        const bool rope = EPI == EPI_QKV_ROPE && p.rope_cos != nullptr;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int col = col0 + g * 64;
+          if (col >= p.N) break;  // uniform over the 4 warps of this column half
+          uint32_t lo[32], hi[32];
+          tmem_ld_32x32b_x32(taddr0 + g * 64, lo);
+          tmem_ld_32x32b_x32(taddr0 + g * 64 + 32, hi);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const int sect = (EPI == EPI_QKV_ROPE) ? col / p.E : 2;
+          const float sc = (EPI == EPI_QKV_ROPE && sect == 0) ? p.q_scale : 1.0f;
+          tmem_wait_ld_dep(lo);
+          reg_fence(hi);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bl = __ldg(b4 + j4), bh = __ldg(b4 + 8 + j4);
+            const float bls[4] = {bl.x, bl.y, bl.z, bl.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;
+              float a = __uint_as_float(lo[j]) + bls[e], b = __uint_as_float(hi[j]) + bhs[e];
+              if constexpr (EPI == EPI_BIAS_GELU) {
+                a = gelu_erf(a);
+                b = gelu_erf(b);
+              } else {
+                a *= sc;
+                b *= sc;
+                if (sect < 2 && rope) {
+                  const float ra = a * rc[j] - b * rs[j], rb = b * rc[j] + a * rs[j];
+                  a = ra;
+                  b = rb;
+                }
+              }
+              lo[j] = __float_as_uint(a);
+              hi[j] = __float_as_uint(b);
+            }
+          }
+#pragma unroll 1
+          for (int part = 0; part < 2; ++part) {
+            uint8_t* stg = smem_stg + (chalf * 2 + (store_iter & 1)) * STG_BYTES;
+            if (issuer) tma_store_wait_read<1>();
+            named_bar_sync(bar_id, 128);
+            const uint32_t srow = smem_u32(stg) + row_local * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t (&src)[32] = c < 4 ? lo : hi;
+              const int o = (c & 3) * 8;
+              uint32_t w4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float y0 = __uint_as_float(src[o + 2 * q]), y1 = __uint_as_float(src[o + 2 * q + 1]);
+                const __half2 h2 = __floats2half2_rn(y0, y1);
+                if (part == 0) {
+                  w4[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                } else {
+                  const float2 f = __half22float2(h2);
+                  w4[q] = pack_half2(y0 - f.x, y1 - f.y);
+                }
+              }
+              const uint32_t addr = srow + (((uint32_t)c ^ (row_local & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]),
+                           "r"(w4[3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (issuer && row0 < p.M) {
+              tma_store_2d(&tmap_out, stg, col + part * p.lo_col_off, row0);
+              tma_store_commit();
+            }
+            ++store_iter;
+          }
+        }
+      } else if constexpr (EPI == EPI_BIAS_GELU || EPI == EPI_GELU_MATHONLY || EPI == EPI_F16_STOREONLY ||
                     EPI == EPI_FMA_MATHONLY) {
         // All four 32-column TMEM loads of this warp's 128 columns are issued back to back and retired by ONE
         // tcgen05.wait::ld: measured on B200 (profiles/r01_epilogue_experiments.txt) every extra ld->wait round trip
@@ -441,16 +527,18 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int EPI>
+template <int EPI, bool SPLIT = false>
 inline cudaError_t launch_gemm2_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout,
                                     const GemmParams& p, int num_sms, cudaStream_t stream) {
   using namespace gemm2_cfg;
-  cudaError_t e = cudaFuncSetAttribute(gemm2_f16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e =
+      cudaFuncSetAttribute(gemm2_f16_kernel<EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
   const int tiles = ((p.M + PAIR_M - 1) / PAIR_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  return launch_pdl(gemm2_f16_kernel<EPI>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, ta, tb, tout, p);
+  return launch_pdl(gemm2_f16_kernel<EPI, SPLIT>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, ta, tb, tout,
+                    p);
 }
 
 }  // namespace esmb200

@@ -32,6 +32,7 @@ struct GemmParams {
   int E;                  // embed dim: columns [0,E) = q, [E,2E) = k, [2E,3E) = v
   float q_scale;          // head_dim^-0.5
   int chunked;            // tile walk: 1 = one contiguous run of tiles per cluster (see gemm2.cuh)
+  int lo_col_off;         // SPLIT kernels with fp16 output: the lo half of column c is written at column c + lo_col_off
 };
 
 

@@ -97,6 +97,7 @@ class LayerBinding:
         if self.head_dim * self.attention_heads != self.embed_dim or self.head_dim > 64 or self.head_dim % 2:
             raise ValueError("esm_b200 supports even head_dim <= 64 (ESM-2 8M/35M/150M/650M/3B); "
                              f"got embed_dim={self.embed_dim}, heads={self.attention_heads}")
+        self.precision = 0  # 0 = fp16 MMA operands, 1 = "fp32x3" (esmb200.h: esmb200_layer_weights.precision)
         self._handle = None
         self._key = None
         self._keep = None
@@ -109,7 +110,7 @@ class LayerBinding:
 
     def handle(self):
         ps = self._params()
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        key = (self.precision,) + tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
         if self._handle is not None and key == self._key:
             return self._handle
         self.release()
@@ -122,6 +123,7 @@ class LayerBinding:
         w = _lib.LayerWeights()
         w.embed_dim, w.num_heads, w.ffn_dim = self.embed_dim, self.attention_heads, self.ffn_embed_dim
         w.head_dim = self.head_dim
+        w.precision = self.precision
         w.ln_eps = self.module.self_attn_layer_norm.eps
         names = [f[0] for f in _lib.LayerWeights._fields_[4:20]]
         for n, p in zip(names, keep):
@@ -165,6 +167,14 @@ class TransformerLayer(nn.Module):
 
     def release(self):
         self._binding.release()
+
+    @property
+    def precision(self) -> int:
+        return self._binding.precision
+
+    @precision.setter
+    def precision(self, value: int):
+        self._binding.precision = int(value)
 
     # ---- reference-facing forward ------------------------------------------------------------------------------
     def forward(self, x, self_attn_mask=None, self_attn_padding_mask=None, need_head_weights=False):
@@ -215,7 +225,7 @@ def run_stack(layers: Sequence, x: torch.Tensor, padding_mask: Optional[torch.Te
     Fdim, H = layers[0].ffn_embed_dim, layers[0].attention_heads
     with torch.cuda.device(x.device):
         handles = (ctypes.c_void_p * n)(*[l.handle() for l in layers])
-        nbytes = lib.esmb200_workspace_bytes(E, H, Fdim, B, T)
+        nbytes = lib.esmb200_workspace_bytes(E, H, Fdim, B, T, getattr(layers[0], "precision", 0))
         ws = _workspace(nbytes, x.device)
         mask = None
         if padding_mask is not None:
@@ -270,6 +280,7 @@ class RobertaLMHead(nn.Module):
         self.bias = nn.Parameter(torch.zeros(output_dim))
         self._packed = None
         self._packed_key = None
+        self._packed_split = None
 
     def forward(self, features):
         x = self.dense(features)
@@ -293,13 +304,47 @@ class RobertaLMHead(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def forward_native(self, x_pre: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float) -> torch.Tensor:
+    def _pack_split(self):
+        """fp32x3 operands of the two GEMMs: fp16 hi | lo halves along K (esmb200_convert_split)."""
+        ps = [self.dense.weight, self.weight]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        if self._packed_split is None or key != self._packed_split[0]:
+            lib = _lib.load()
+            E = self.dense.weight.shape[1]
+            V = self.weight.shape[0]
+            npad = (V + 63) // 64 * 64
+            dev = self.weight.device
+            wd32 = _f32(self.dense.weight)
+            wo32 = torch.zeros((npad, E), dtype=torch.float32, device=dev)
+            wo32[:V] = self.weight.detach().float()
+            wd = torch.empty((E, 2 * E), dtype=torch.float16, device=dev)
+            wo = torch.empty((npad, 2 * E), dtype=torch.float16, device=dev)
+            _lib.check(lib.esmb200_convert_split(_ptr(wd32), _ptr(wd), E, E, _stream()))
+            _lib.check(lib.esmb200_convert_split(_ptr(wo32), _ptr(wo), npad, E, _stream()))
+            self._packed_split = (key, wd, wo)
+        return self._packed_split[1], self._packed_split[2]
+
+    def forward_native(self, x_pre: torch.Tensor, ln_w: torch.Tensor, ln_b: torch.Tensor, eps: float,
+                       precision: int = 0) -> torch.Tensor:
         """x_pre: fp32 [B,T,E] residual stream before emb_layer_norm_after (esm2.py:123). Returns logits [B,T,V]."""
         lib = _lib.load()
         B, T, E = x_pre.shape
         M = B * T
         dev = x_pre.device
         w_dense, w_out, b_out, V, npad, b_dense, ln2_w, ln2_b = self._pack()
+        if precision:
+            wd, wo = self._pack_split()
+            a16 = torch.empty((M, 2 * E), dtype=torch.float16, device=dev)
+            _lib.check(lib.esmb200_layernorm_split(_ptr(x_pre), _ptr(ln_w), _ptr(ln_b), _ptr(a16), M, E, eps, _stream()))
+            h = torch.empty((M, E), dtype=torch.float32, device=dev)
+            _lib.check(lib.esmb200_gemm_split(_lib.EPI_BIAS_GELU_F32, _ptr(a16), _ptr(wd), _ptr(b_dense), _ptr(h), M, E, E,
+                                              None, None, 0, 0, _stream()))
+            _lib.check(lib.esmb200_layernorm_split(_ptr(h), _ptr(ln2_w), _ptr(ln2_b), _ptr(a16), M, E,
+                                                   self.layer_norm.eps, _stream()))
+            logits = torch.empty((M, npad), dtype=torch.float32, device=dev)
+            _lib.check(lib.esmb200_gemm_split(_lib.EPI_BIAS_F32, _ptr(a16), _ptr(wo), _ptr(b_out), _ptr(logits), M, npad, E,
+                                              None, None, 0, 0, _stream()))
+            return logits.view(B, T, npad)[:, :, :V].contiguous()
         a16 = torch.empty((M, E), dtype=torch.float16, device=dev)
         _lib.check(lib.esmb200_layernorm_f16(_ptr(x_pre), _ptr(ln_w), _ptr(ln_b), _ptr(a16), M, E, eps, _stream()))
         h = torch.empty((M, E), dtype=torch.float32, device=dev)
@@ -420,6 +465,24 @@ class ESM2(nn.Module):
         self.lm_head = RobertaLMHead(embed_dim, self.alphabet_size, self.embed_tokens.weight)
         self._rope_cache = None
         self._mirrors: Dict[str, tuple] = {}
+        self.precision = "fp16"
+
+    PRECISIONS = {"fp16": 0, "fp32x3": 1}
+
+    def set_precision(self, name: str) -> "ESM2":
+        """"fp16" (default): fp16 MMA operands, fp32 accumulation — the fast path bench.py measures.
+        "fp32x3": every MMA operand (LayerNorm output, weights, q, k, v, softmax probabilities, context, FFN hidden) is
+        an fp16 hi + lo pair and every product runs hi*hi + lo*hi + hi*lo into the fp32 accumulator: 22 significand bits
+        per operand, fp32-grade parity with the reference at ~3x the tensor work.  Needs
+        embed_dim % 64 == 0."""
+        if name not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}")
+        if name == "fp32x3" and self.embed_dim % 64 != 0:
+            raise ValueError("fp32x3 precision needs embed_dim % 64 == 0")
+        self.precision = name
+        for layer in self.layers:
+            layer.precision = self.PRECISIONS[name]
+        return self
 
     def _rope_tables(self, T: int):
         inv = self.layers[0].self_attn.rot_emb.inv_freq
@@ -484,7 +547,7 @@ class ESM2(nn.Module):
             # esm2.py:129 LM head, from the pre-LN stream (its first step is the same emb_layer_norm_after)
             ln = self.emb_layer_norm_after
             ln_w, ln_b = self._mirror("ln_after.w", ln.weight), self._mirror("ln_after.b", ln.bias)
-            logits = cast(self.lm_head.forward_native(x, ln_w, ln_b, ln.eps))
+            logits = cast(self.lm_head.forward_native(x, ln_w, ln_b, ln.eps, self.PRECISIONS[self.precision]))
             # esm2.py:123-128 final LayerNorm; the last representation is post-LN
             _lib.check(lib.esmb200_layernorm(_ptr(x), _ptr(ln_w), _ptr(ln_b), _ptr(x), B * T, E, ln.eps, _stream()))
         if N in repr_layers:

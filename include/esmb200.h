@@ -64,6 +64,10 @@ typedef struct esmb200_layer_weights {
   const float* fc2_bias;   /* fc2.bias   [E]   */
   int32_t head_dim;        /* 0 = E / H. Even values <= 64: 16 / 24 / 32 (ESM-2 8M / 35M / 150M) run in zero-padded
                             * 64-wide head slots of the attention-side tensors; 64 = 650M / 3B / MSA Transformer */
+  int32_t precision;       /* 0 = fp16 MMA operands (default). 1 = "fp32x3": every MMA operand (activations, weights,
+                            * q, k, v, P) is an fp16 hi | lo pair and every product runs hi*hi + lo*hi + hi*lo into the
+                            * fp32 accumulator (22 significand bits per operand) — fp32-grade results at ~3x the tensor
+                            * work; needs E % 64 == 0; not available on the MSA axial path */
 } esmb200_layer_weights;
 
 int esmb200_abi_version(void);
@@ -75,7 +79,8 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
 int esmb200_layer_destroy(esmb200_layer* layer);
 
 /* Scratch bytes needed by esmb200_layer_forward / esmb200_stack_forward for a [B,T] batch. */
-size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t num_heads, int32_t ffn_dim, int32_t B, int32_t T);
+size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t num_heads, int32_t ffn_dim, int32_t B, int32_t T,
+                               int32_t precision);
 
 /* One TransformerLayer.forward (modules.py:120-142), in place on x:
  *     x += out_proj(attention(rope(q_proj(LN1 x) * d^-1/2), rope(k_proj(LN1 x)), v_proj(LN1 x)));
@@ -215,6 +220,21 @@ int esmb200_profile_read(int32_t* tags, float* ms, int32_t max_records);
 
 /* fp32 -> fp16 elementwise */
 int esmb200_convert_f16(const float* src, void* dst_f16, size_t n, void* stream);
+
+/* ---- fp32x3 precision building blocks (operands as fp16 hi | lo pairs along K): the LM head and kernel-level tests.
+ * esmb200_layernorm_split: fp32 [M,E] -> LayerNorm -> fp16 [M,2E] (hi in columns [0,E), lo = rn(y - hi) in [E,2E)).
+ * esmb200_convert_split:   fp32 [rows,K] -> fp16 [rows,2K] the same way (weights).
+ * esmb200_gemm_split:      esmb200_gemm_f16 with a [M,2K], w [N,2K]; fp16 outputs (QKV_ROPE, BIAS_GELU) are written as
+ *                          [M,2N] hi | lo, fp32 outputs as [M,N].  K % 64 == 0.
+ * esmb200_attention_split: esmb200_attention on qkv [B*T, 6E] = [q k v]_hi | [q k v]_lo -> ctx [B*T, 2E] hi | lo. */
+int esmb200_layernorm_split(const float* x, const float* weight, const float* bias, void* out_f16, int32_t M, int32_t E,
+                            float eps, void* stream);
+int esmb200_convert_split(const float* src, void* dst_f16, int64_t rows, int32_t K, void* stream);
+int esmb200_gemm_split(int32_t epilogue, const void* a, const void* w, const float* bias, void* out, int32_t M,
+                       int32_t N, int32_t K, const float* rope_cos, const float* rope_sin, int32_t T, int32_t E,
+                       void* stream);
+int esmb200_attention_split(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,
+                            int32_t H, void* scratch, void* stream);
 
 /* ---- process-wide kernel selection knobs (A/B measurements; the defaults are the product configuration) ----
  * "attn"      8 (default: attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, 2 CTAs/SM)          env ESMB200_ATTN

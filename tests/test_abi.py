@@ -32,10 +32,11 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_workspace_size_is_pure_host_arithmetic():
     from esm_b200 import _lib
     lib = _lib.load()
-    small = lib.esmb200_workspace_bytes(1280, 20, 5120, 1, 1024)
-    big = lib.esmb200_workspace_bytes(1280, 20, 5120, 256, 1024)
+    small = lib.esmb200_workspace_bytes(1280, 20, 5120, 1, 1024, 0)
+    big = lib.esmb200_workspace_bytes(1280, 20, 5120, 256, 1024, 0)
     assert 0 < small < big
     assert big >= 256 * 1024 * (1280 * 2 + 5120 * 2)  # xn + h
+    assert lib.esmb200_workspace_bytes(1280, 20, 5120, 256, 1024, 1) >= 2 * 256 * 1024 * (1280 * 2 + 5120 * 2)  # fp32x3
 
 
 def test_product_package_never_imports_the_oracle():
