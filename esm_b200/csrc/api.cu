@@ -144,7 +144,7 @@ int attn_version() {
 int attn_poly() {
   if (g_attn_poly < 0) {
     const char* e = getenv("ESMB200_ATTN_POLY");
-    g_attn_poly = (e && (e[0] == '0' || e[0] == '2' || e[0] == '3' || e[0] == '4')) ? (e[0] - '0') : 3;
+    g_attn_poly = (e && (e[0] == '0' || e[0] == '2' || e[0] == '3' || e[0] == '4')) ? (e[0] - '0') : 4;
   }
   return g_attn_poly;
 }
@@ -156,8 +156,8 @@ cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, 
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
     case 2: return launch_attention_v8_poly<2>(tq, tkv, ap, sms, st);
-    case 4: return launch_attention_v8_poly<4>(tq, tkv, ap, sms, st);
-    default: return launch_attention_v8_poly<3>(tq, tkv, ap, sms, st);
+    case 3: return launch_attention_v8_poly<3>(tq, tkv, ap, sms, st);
+    default: return launch_attention_v8_poly<4>(tq, tkv, ap, sms, st);
   }
 }
 

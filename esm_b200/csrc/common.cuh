@@ -491,6 +491,15 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, f
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

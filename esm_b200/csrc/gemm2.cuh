@@ -333,14 +333,25 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   return y;
                 } else return gelu_erf(x);
               };
-              const uint32_t o0 = pack_half2(act(__uint_as_float(a[8 * v + 0]) + b0.x),
-                                             act(__uint_as_float(a[8 * v + 1]) + b0.y));
-              const uint32_t o1 = pack_half2(act(__uint_as_float(a[8 * v + 2]) + b0.z),
-                                             act(__uint_as_float(a[8 * v + 3]) + b0.w));
-              const uint32_t o2 = pack_half2(act(__uint_as_float(a[8 * v + 4]) + b1.x),
-                                             act(__uint_as_float(a[8 * v + 5]) + b1.y));
-              const uint32_t o3 = pack_half2(act(__uint_as_float(a[8 * v + 6]) + b1.z),
-                                             act(__uint_as_float(a[8 * v + 7]) + b1.w));
+              uint32_t o0, o1, o2, o3;
+              if constexpr (EPI == EPI_BIAS_GELU) {  // product path: packed f32x2 GELU
+                float y[8], xb[8];
+                add2(xb[0], xb[1], __uint_as_float(a[8 * v + 0]), __uint_as_float(a[8 * v + 1]), b0.x, b0.y);
+                add2(xb[2], xb[3], __uint_as_float(a[8 * v + 2]), __uint_as_float(a[8 * v + 3]), b0.z, b0.w);
+                add2(xb[4], xb[5], __uint_as_float(a[8 * v + 4]), __uint_as_float(a[8 * v + 5]), b1.x, b1.y);
+                add2(xb[6], xb[7], __uint_as_float(a[8 * v + 6]), __uint_as_float(a[8 * v + 7]), b1.z, b1.w);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gelu_erf2(xb[2 * q], xb[2 * q + 1], y[2 * q], y[2 * q + 1]);
+                o0 = pack_half2(y[0], y[1]);
+                o1 = pack_half2(y[2], y[3]);
+                o2 = pack_half2(y[4], y[5]);
+                o3 = pack_half2(y[6], y[7]);
+              } else {
+                o0 = pack_half2(act(__uint_as_float(a[8 * v + 0]) + b0.x), act(__uint_as_float(a[8 * v + 1]) + b0.y));
+                o1 = pack_half2(act(__uint_as_float(a[8 * v + 2]) + b0.z), act(__uint_as_float(a[8 * v + 3]) + b0.w));
+                o2 = pack_half2(act(__uint_as_float(a[8 * v + 4]) + b1.x), act(__uint_as_float(a[8 * v + 5]) + b1.y));
+                o3 = pack_half2(act(__uint_as_float(a[8 * v + 6]) + b1.z), act(__uint_as_float(a[8 * v + 7]) + b1.w));
+              }
               if constexpr (EPI == EPI_GELU_MATHONLY || EPI == EPI_FMA_MATHONLY) {
                 sink ^= o0 ^ o1 ^ o2 ^ o3;
               } else {

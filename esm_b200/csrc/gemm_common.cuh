@@ -54,5 +54,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - q : q);
 }
 
+// The same for two values at once with packed f32x2 arithmetic (FFMA2 / FMUL2): ~20 issue slots per pair instead of 30.
+// The fc1 epilogue is instruction-energy bound under the 1 kW cap (profiles/r01_epilogue_experiments.txt).
+__device__ __forceinline__ void gelu_erf2(float x0, float x1, float& y0, float& y1) {
+  constexpr float PC = 0.3275911f * 0.70710678118654752440f;
+  float d0, d1, p0, p1, s0, s1, q0, q1, r0, r1, t0, t1;
+  fma2(d0, d1, fabsf(x0), fabsf(x1), PC, PC, 1.0f, 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  fma2(p0, p1, t0, t1, 0.5f * 1.061405429f, 0.5f * 1.061405429f, 0.5f * -1.453152027f, 0.5f * -1.453152027f);
+  fma2(p0, p1, p0, p1, t0, t1, 0.5f * 1.421413741f, 0.5f * 1.421413741f);
+  fma2(p0, p1, p0, p1, t0, t1, 0.5f * -0.284496736f, 0.5f * -0.284496736f);
+  fma2(p0, p1, p0, p1, t0, t1, 0.5f * 0.254829592f, 0.5f * 0.254829592f);
+  mul2(p0, p1, p0, p1, t0, t1);
+  mul2(s0, s1, x0, x1, -0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f);
+  mul2(s0, s1, s0, s1, x0, x1);  // -x^2/2 * log2(e)
+  mul2(q0, q1, p0, p1, ex2_approx(s0), ex2_approx(s1));
+  mul2(q0, q1, q0, q1, x0, x1);                   // x * q
+  fma2(r0, r1, q0, q1, -1.0f, -1.0f, x0, x1);     // x - x * q
+  y0 = x0 >= 0.f ? r0 : q0;
+  y1 = x1 >= 0.f ? r1 : q1;
+}
 
 }  // namespace esmb200

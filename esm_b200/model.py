@@ -408,7 +408,7 @@ class ContactPredictionHead(nn.Module):
             u = (a1f * (wl.reshape(1, L * H, 1) / a12)).contiguous()
             bias = _f32(self.regression.bias) if self.regression.bias is not None else None
             out = torch.empty((B, S, S), dtype=torch.float32, device=dev)
-            _lib.check(lib.esmb200_contact_finalize(_ptr(acc), _ptr(u), _ptr(a1f), bias, _ptr(out), B, L * H, S, _stream()))
+            _lib.check(lib.esmb200_contact_finalize(_ptr(acc), _ptr(u), _ptr(a1f), _ptr(bias), _ptr(out), B, L * H, S, _stream()))
         return out
 
     def _forward_torch(self, tokens, attentions, w, lo, hi):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU session B: whole GPU test suite (new parity / drop-in / narrow-head tests), bench with the extra legs
 mkdir -p gpurun_out
-echo "== full gpu suite"; timeout 1500 python -m pytest tests -x -q -m gpu -s > gpurun_out/b_tests.log 2>&1; echo "rc=$?"; grep -E "PARITY|passed|failed|Error|error" gpurun_out/b_tests.log | tail -40
+echo "== full gpu suite"; timeout 1500 python -m pytest tests -q -m gpu -s > gpurun_out/b_tests.log 2>&1; echo "rc=$?"; grep -E "PARITY|passed|failed|Error|error" gpurun_out/b_tests.log | tail -40
 echo "== bench full"; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/b_bench.json 2> gpurun_out/b_bench.err; echo "rc=$?"; tail -3 gpurun_out/b_bench.err; python - <<'PY'
 import json
 d=json.load(open('gpurun_out/b_bench.json'))

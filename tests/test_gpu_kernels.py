@@ -204,6 +204,6 @@ def test_error_reporting(dev):
     L = _lib(); lib = L.load()
     a = torch.zeros(128, 100, dtype=torch.float16, device=dev)
     rc = lib.esmb200_gemm_f16(L.EPI_BIAS_F32, P(a), P(a), P(a), P(a), 128, 128, 100, None, None, 0, 0, S())
-    assert rc == -1 and b"K % 64" in lib.esmb200_last_error()
+    assert rc == -1 and b"K % 8" in lib.esmb200_last_error()
     with pytest.raises(L.Esmb200Error):
         L.check(rc)
