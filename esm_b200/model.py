@@ -187,7 +187,10 @@ def layer_forward(binding: LayerBinding, x, self_attn_mask=None, self_attn_paddi
     if self_attn_mask is not None:
         raise NotImplementedError("ESM-2 never passes self_attn_mask (esm2.py:112-116)")
     T, B, E = x.shape
-    xb = x.transpose(0, 1).contiguous().float()  # (B,T,E) batch-major copy, updated in place
+    # (B,T,E) batch-major PRIVATE copy, updated in place.  Layer 0 of the reference receives a transposed view of the
+    # tensor it also returns as representations[0] (esm2.py:99-106): contiguous()/float() would hand that storage back.
+    xb = torch.empty((B, T, E), dtype=torch.float32, device=x.device)
+    xb.copy_(x.transpose(0, 1))
     cos, sin = rope_tables(binding.module.self_attn.rot_emb.inv_freq, T)
     attn = run_stack([binding], xb, self_attn_padding_mask, cos, sin, None, [0] if need_head_weights else [])
     out = xb.transpose(0, 1).to(x.dtype)
