@@ -433,7 +433,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n, bo
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// process-wide switch: -1 = not read yet (environment ESMB200_PDL, default on); esmb200_set_option("pdl", v) overrides
+// process-wide switch: -1 = not read yet (environment ESMB200_PDL, default OFF); esmb200_set_option("pdl", v) overrides.
+// Measured on B200 (scripts/pdl_ab.py, profiles/r02_pdl_ab.json): alternating on/off inside one process, the 33-layer
+// forward takes 54.07 / 53.93 ms (B=32) and 423.4 / 421.1 ms (B=256) with / without the attribute — the kernels are
+// persistent, so every CTA of a kernel ends within microseconds of the others and there is no tail to overlap the next
+// prologue with, while early-resident dependents spin in griddepcontrol.wait.  Kept as an option, off by default.
 inline int& pdl_flag() {
   static int flag = -1;
   return flag;
@@ -442,7 +446,7 @@ inline bool pdl_enabled() {
   int& f = pdl_flag();
   if (f < 0) {
     const char* e = getenv("ESMB200_PDL");
-    f = (e && e[0] == '0') ? 0 : 1;
+    f = (e && e[0] == '1') ? 1 : 0;
   }
   return f != 0;
 }
