@@ -83,6 +83,13 @@ class LayerWeights(ctypes.Structure):
     ]
 
 
+class ContactJob(ctypes.Structure):
+    """struct esmb200_contact_job"""
+
+    _fields_ = [("weights", c_void_p), ("keep", c_void_p), ("acc", c_void_p), ("row_part", c_void_p),
+                ("col_part", c_void_p), ("lo", c_int32), ("hi", c_int32)]
+
+
 class Esmb200Error(RuntimeError):
     pass
 
@@ -106,8 +113,8 @@ def _declare(lib):
                                           c_void_p, c_void_p, c_size_t, c_void_p]
     lib.esmb200_stack_forward.restype = c_int32
     lib.esmb200_stack_forward.argtypes = [POINTER(c_void_p), c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
-                                          c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int32, c_void_p, c_size_t,
-                                          c_void_p]
+                                          c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int32,
+                                          POINTER(ContactJob), c_void_p, c_size_t, c_void_p]
     lib.esmb200_embed_tokens.restype = c_int32
     lib.esmb200_embed_tokens.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                          c_int32, c_void_p]

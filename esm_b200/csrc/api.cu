@@ -20,6 +20,7 @@
 
 #include "attention7.cuh"
 #include "attention8.cuh"
+#include "attention_contact.cuh"
 #include "attention_probs.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
@@ -161,6 +162,14 @@ cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, 
   }
 }
 
+int qkv_chunked() {  // tile walk of the QKV GEMM (gemm2.cuh): 1 = one contiguous run of tiles per cluster (default)
+  static const int v = [] {
+    const char* e = getenv("ESMB200_QKV_CHUNKED");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v;
+}
+
 constexpr int kMaxDevices = 64;
 
 int num_sms() {  // per device: one process may drive several GPUs
@@ -264,8 +273,19 @@ int run_key_bits(const uint8_t* pad_mask, const AttnScratch& s, int B, int T, cu
   return ESMB200_OK;
 }
 
+// contact-head accumulators of ONE layer (esmb200_contact_job resolved for layer i)
+struct ContactLayer {
+  const float* w;
+  const uint8_t* keep;
+  float* acc;
+  float* row_part;
+  float* col_part;
+  int lo, S;
+};
+
 int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batch_stride, int attn_flags,
-                  const AttnScratch& s, int B, int T, int H, cudaStream_t st, bool split = false) {
+                  const AttnScratch& s, int B, int T, int H, cudaStream_t st, bool split = false,
+                  const ContactLayer* contact = nullptr) {
   const int E = H * 64;
   const uint64_t qcols = (uint64_t)(split ? 6 : 3) * E;  // fp32x3: [q k v]_hi | [q k v]_lo
   CUtensorMap tq;
@@ -287,6 +307,24 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
     e = launch_attention_fwd(tq, tkv, ap, num_sms(), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "attention launch");
+  if (probs && contact && !split) {
+    // probabilities written once and folded into the contact accumulators in the same pass (attention_contact.cuh)
+    if (B > 65535) return fail(ESMB200_EINVAL, "return_contacts: B must be <= 65535");
+    ContactFuseParams cp;
+    cp.B = B; cp.T = T; cp.H = H; cp.E = E;
+    cp.keybits = s.keybits; cp.kvlen = s.kvlen; cp.words = s.words;
+    cp.row_max = s.row_max; cp.row_sum = s.row_sum; cp.probs = probs;
+    cp.batch_stride = probs_batch_stride > 0 ? probs_batch_stride : (long long)H * T * T;
+    cp.zero_pad_rows = attn_flags & 1;
+    cp.w = contact->w; cp.keep = contact->keep; cp.acc = contact->acc;
+    cp.row_part = contact->row_part; cp.col_part = contact->col_part; cp.lo = contact->lo; cp.S = contact->S;
+    {
+      ProfScope ps(T_PROBS, st);
+      e = launch_attention_probs_contact(tq, cp, st);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "attention probs+contact launch");
+    return ESMB200_OK;
+  }
   if (probs) {
     if ((size_t)B * H > 65535) return fail(ESMB200_EINVAL, "need_head_weights: B*H must be <= 65535");
     ProbsParams pp;
@@ -504,7 +542,7 @@ struct ActMaps {
 
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
                        float* attn_probs, long long attn_batch_stride, int attn_flags, const Workspace& ws,
-                       const ActMaps& am, cudaStream_t st) {
+                       const ActMaps& am, cudaStream_t st, const ContactLayer* contact = nullptr) {
   const int E = L->E, F = L->F, H = L->H, Ea = L->Ea;
   const int M = B * T;
   const bool split = L->split != 0;
@@ -520,12 +558,12 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   GemmParams g;
   memset(&g, 0, sizeof g);
   g.M = M; g.N = 3 * Ea; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * Ea;
-  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = Ea; g.q_scale = L->q_scale; g.chunked = 1;
+  g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = Ea; g.q_scale = L->q_scale; g.chunked = qkv_chunked();
   g.lo_col_off = 3 * Ea;
   int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV, split);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
-  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st, split);
+  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st, split, contact);
   if (rc) return rc;
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
@@ -565,9 +603,18 @@ int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int H
 int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float* x, const uint8_t* pad_mask,
                           int32_t B, int32_t T, const float* rope_cos, const float* rope_sin,
                           float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride,
-                          int32_t attn_flags, void* workspace, size_t workspace_bytes, void* stream) {
+                          int32_t attn_flags, const esmb200_contact_job* contact, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   if (!layers || n_layers <= 0 || !x || !rope_cos || !rope_sin || !workspace)
     return fail(ESMB200_EINVAL, "null argument");
+  if (contact) {
+    if (!attn_out) return fail(ESMB200_EINVAL, "a contact job needs attn_out for every layer");
+    for (int i = 0; i < n_layers; ++i)
+      if (!attn_out[i]) return fail(ESMB200_EINVAL, "a contact job needs attn_out for every layer");
+    if (!contact->weights || !contact->acc || !contact->row_part || !contact->col_part || contact->lo < 0 ||
+        contact->hi > T || contact->hi <= contact->lo)
+      return fail(ESMB200_EINVAL, "bad contact job");
+  }
   if (B <= 0 || T <= 0) return fail(ESMB200_EINVAL, "empty batch");
   if ((long long)B * T > 0x7fffffffLL / 8) return fail(ESMB200_EINVAL, "B*T too large for one call; split the batch");
   int rc = check_device();
@@ -587,9 +634,18 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   if (rc) return rc;
   rc = run_key_bits(pad_mask, ws.as, B, T, st);
   if (rc) return rc;
+  const int nt128 = (T + 127) / 128;
   for (int i = 0; i < n_layers; ++i) {
+    ContactLayer cl;
+    if (contact) {
+      const int S = contact->hi - contact->lo;
+      const size_t part = (size_t)B * H * nt128 * S;
+      cl.w = contact->weights + (size_t)i * H; cl.keep = contact->keep; cl.acc = contact->acc;
+      cl.row_part = contact->row_part + (size_t)i * part; cl.col_part = contact->col_part + (size_t)i * part;
+      cl.lo = contact->lo; cl.S = S;
+    }
     rc = layer_forward_impl(layers[i], x, B, T, rope_cos, rope_sin, attn_out ? attn_out[i] : nullptr, attn_batch_stride,
-                            attn_flags, ws, am, st);
+                            attn_flags, ws, am, st, contact ? &cl : nullptr);
     if (rc) return rc;
     if (repr_out && repr_out[i])
       CK(cudaMemcpyAsync(repr_out[i], x, (size_t)B * T * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -604,7 +660,7 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
   float* attn_arr[1] = {attn_probs};
   esmb200_layer* arr[1] = {layer};
   return esmb200_stack_forward(arr, 1, x, pad_mask, B, T, rope_cos, rope_sin, nullptr, attn_probs ? attn_arr : nullptr,
-                               0, 0, workspace, workspace_bytes, stream);
+                               0, 0, nullptr, workspace, workspace_bytes, stream);
 }
 
 int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, int32_t B, int32_t T, int32_t E,

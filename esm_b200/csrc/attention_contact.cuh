@@ -1,0 +1,256 @@
+// esm_b200 — need_head_weights + return_contacts in ONE pass (sm_100a, head_dim 64): the attention probabilities of a
+// layer are written to the stacked [B,L,H,T,T] result AND folded into the contact head's accumulators while they are
+// still in registers, so the 4*B*L*H*T^2-byte stack (24 GB at BASELINE.json configs[3]) is written once and never read
+// back.  r01 / attention_probs.cuh + contact_accumulate_kernel wrote it and re-read it (17 % + 14 % of configs[3]).
+//
+// Replaces /root/reference/esm/multihead_attention.py:397-400 (per-head probabilities) and the per-layer share of
+// ContactPredictionHead.forward, /root/reference/esm/modules.py:338-357 (eos masking, bos/eos crop, symmetrize :27-29,
+// apc :32-41), in the restated form of elementwise.cuh: with A_h the masked, cropped map of head h,
+//     acc[b,i,j]        += sum_h w_h A_h[i,j]                  (one owner CTA per tile: plain read-modify-write)
+//     row_part[b,h,kt,i] = sum_{j in key tile kt} A_h[i,j]     (partials over the key tiles, summed by the caller)
+//     col_part[b,h,qt,j] = sum_{i in query tile qt} A_h[i,j]   (partials over the query tiles)
+// No atomics: every output element has one writer and every sum a fixed order -> bit-reproducible contacts.
+//
+// One CTA = (128-key tile, 128-query tile, sequence) and LOOPS OVER THE HEADS: warp 4 lane 0 streams (Q_h, K_h) tiles
+// through a 2-stage TMA ring and issues S_h = Q_h K_h^T (4 x UMMA 128x128x16) into a double-buffered TMEM accumulator;
+// warps 0-3 (thread = query row) turn S_h into p = exp(s - m) / l with the statistics saved by the forward kernel, write
+// the tile through a padded shared-memory transpose (every global store is a 128-byte row segment) and accumulate.
+#pragma once
+
+#include "attention_common.cuh"
+
+namespace esmb200 {
+
+struct ContactFuseParams {
+  int B, T, H, E;            // E = 64 * H
+  const uint32_t* keybits;   // [B, words]
+  const int* kvlen;          // [B]
+  int words;
+  const float* row_max;      // [B,H,T] reference max / row sum of the forward kernel
+  const float* row_sum;
+  float* probs;              // this layer's slice of the stacked result: batch b at probs + b * batch_stride
+  long long batch_stride;
+  int zero_pad_rows;
+  // contact head
+  const float* w;            // [H] regression weights of this layer's heads
+  const uint8_t* keep;       // [B,T] 1 = not <eos>, or NULL
+  float* acc;                // [B,S,S]
+  float* row_part;           // [B,H,nkt,S]
+  float* col_part;           // [B,H,nqt,S]
+  int lo, S;                 // cropped positions [lo, lo+S)
+};
+
+namespace cfuse_cfg {
+constexpr int BLOCK = 128;            // query rows and keys per tile
+constexpr int NUM_THREADS = 160;      // warps 0-3: one thread per query row; warp 4: TMA + MMA issuer
+constexpr int STAGES = 2;
+constexpr int TILE_BYTES = attn_cfg::TILE_BYTES;
+constexpr int TMEM_COLS = 256;        // S double buffer
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 4 * 32 * 33 * 4 /*transpose*/ +
+                           2 * 4 * 128 * 4 /*column partials, double buffered*/ + 128 * 4 /*row keep flags*/;
+}  // namespace cfuse_cfg
+
+__global__ void __launch_bounds__(cfuse_cfg::NUM_THREADS, 2)
+attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const ContactFuseParams p) {
+  using namespace cfuse_cfg;
+  constexpr float LOG2E = attn_cfg::LOG2E;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                             // [STAGES]
+  uint8_t* smem_k = smem + STAGES * TILE_BYTES;       // [STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * TILE_BYTES);
+  uint64_t* full = bars;         // [2] TMA -> MMA
+  uint64_t* empty = bars + 2;    // [2] MMA done with the stage -> TMA
+  uint64_t* s_full = bars + 4;   // [2] MMA -> softmax
+  uint64_t* s_free = bars + 6;   // [2] softmax -> MMA (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * TILE_BYTES + 128);  // [4][32*33]
+  float* colw = tiles + 4 * 32 * 33;                                              // [2][4][128]
+  float* rowkeep = colw + 2 * 4 * 128;                                            // [128]
+
+  const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int kt = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * BLOCK, k0 = kt * BLOCK;
+  const int row_base = b * p.T;
+  const int nkt = gridDim.x, nqt = gridDim.y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_s = *tmem_slot;
+  const bool live = k0 < p.kvlen[b];  // otherwise every key of this tile is masked: all probabilities are exactly 0
+
+  if (warp == 4) {
+    // ===================== TMA producer + MMA issuer =====================
+    if (lane == 0 && live) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, 128, false);
+      auto load = [&](int h) {
+        const int s = h & 1;
+        mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
+        tma_load_2d(smem_q + s * TILE_BYTES, &tmap_qkv, &full[s], h * 64, row_base + q0);
+        tma_load_2d(smem_k + s * TILE_BYTES, &tmap_qkv, &full[s], p.E + h * 64, row_base + k0);
+      };
+      load(0);
+      if (p.H > 1) load(1);
+      for (int h = 0; h < p.H; ++h) {
+        const int s = h & 1;
+        const uint32_t ph = (h >> 1) & 1;
+        mbar_wait(&full[s], ph);
+        if (h >= 2) mbar_wait(&s_free[s], ((h - 2) >> 1) & 1);  // the softmax threads have read S of head h-2
+        tc_fence_after();
+        const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q + s * TILE_BYTES), 1024, 0);
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * TILE_BYTES), 1024, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_s + s * 128, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0);
+        tc_commit(&s_full[s]);
+        tc_commit(&empty[s]);
+        if (h + 2 < p.H) {
+          mbar_wait(&empty[s], ph);  // the MMAs of head h have read the stage
+          load(h + 2);
+        }
+      }
+    }
+  } else {
+    // ===================== probabilities + contact accumulation: one thread per query row =====================
+    const uint32_t lane_addr = (warp * 32u) << 16;
+    const int t = q0 + (int)threadIdx.x;          // this thread's query position
+    const bool row_ok = t < p.T;
+    const int ncols = min(BLOCK, p.T - k0);
+    const int hi = p.lo + p.S;
+    const uint8_t* kp = p.keep ? p.keep + (size_t)b * p.T : nullptr;
+    // contact masks: position kept (not <eos>) and inside the bos/eos crop
+    const bool ri = row_ok && t >= p.lo && t < hi && (!kp || kp[t]);
+    rowkeep[threadIdx.x] = ri ? 1.f : 0.f;
+    uint32_t cmask[4], kw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = k0 + c * 32 + (int)lane;
+      const bool kj = j < p.T && j >= p.lo && j < hi && (!kp || kp[j]);
+      cmask[c] = __ballot_sync(0xffffffffu, kj);
+    }
+    if (live) {
+      const uint4 kw4 = __ldg(reinterpret_cast<const uint4*>(p.keybits + (size_t)b * p.words + kt * 4));
+      kw[0] = kw4.x; kw[1] = kw4.y; kw[2] = kw4.z; kw[3] = kw4.w;
+    }
+    const bool qpad = p.zero_pad_rows && row_ok && !((p.keybits[(size_t)b * p.words + (t >> 5)] >> (t & 31)) & 1u);
+    named_bar_sync(1, 128);  // rowkeep visible to the four warps
+    float* tile = tiles + warp * (32 * 33);
+    const int t_warp0 = q0 + (int)warp * 32;
+    const int nrows = min(32, p.T - t_warp0);
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+
+    for (int h = 0; h < p.H; ++h) {
+      const int s = h & 1;
+      const float wh = __ldg(p.w + h);
+      float mneg = 0.f, inv = 0.f;
+      if (live) {
+        const size_t si = ((size_t)b * p.H + h) * p.T + (row_ok ? t : 0);
+        mneg = -p.row_max[si] * LOG2E;
+        const float l = p.row_sum[si];
+        inv = (l > 0.f && !qpad) ? 1.0f / l : 0.f;  // esm2.py:135-139: rows of padded query tokens are zero
+        mbar_wait(&s_full[s], (h >> 1) & 1);
+        tc_fence_after();
+      }
+      float* base = p.probs + (size_t)b * p.batch_stride + (size_t)h * p.T * p.T + k0;
+      float rs = 0.f;
+      float colp[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        colp[c] = 0.f;
+        if (c * 32 >= ncols) continue;  // uniform
+        if (live) {
+          uint32_t sv[32];
+          tmem_ld_32x32b_x32(tmem_s + lane_addr + s * 128 + c * 32, sv);
+          tmem_wait_ld_dep(sv);
+          const uint32_t wd = kw[c], cm = cmask[c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pr = ((wd >> i) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, mneg)) * inv : 0.f;
+            tile[lane * 33 + i] = pr;
+            const float x = (ri && ((cm >> i) & 1u)) ? pr : 0.f;
+            acc[c * 32 + i] = fmaf(wh, x, acc[c * 32 + i]);
+            rs += x;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = 0.f;
+        }
+        __syncwarp();
+        const int col = c * 32 + (int)lane;
+        float cs = 0.f;
+        if (col < ncols) {
+          for (int r = 0; r < nrows; ++r) {
+            const float v = tile[r * 33 + lane];
+            base[(size_t)(t_warp0 + r) * p.T + col] = v;
+            cs = fmaf(v, rowkeep[warp * 32 + r], cs);
+          }
+        }
+        colp[c] = ((cmask[c] >> lane) & 1u) ? cs : 0.f;
+        __syncwarp();
+      }
+      if (live) {
+        tc_fence_before();
+        mbar_arrive(&s_free[s]);  // S_h has been read: the MMA of head h+2 may overwrite this buffer
+      }
+      // row partial of this key tile; column partials of this query tile (4 warps summed in a fixed order)
+      if (row_ok && t >= p.lo && t < hi) p.row_part[(((size_t)b * p.H + h) * nkt + kt) * p.S + (t - p.lo)] = rs;  // 0 for <eos>
+      float* cw = colw + (h & 1) * (4 * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cw[warp * 128 + c * 32 + lane] = colp[c];
+      named_bar_sync(1, 128);
+      {
+        const int j = k0 + (int)threadIdx.x;
+        if (j >= p.lo && j < hi && j < p.T) {
+          const float tsum = (cw[threadIdx.x] + cw[128 + threadIdx.x]) + (cw[256 + threadIdx.x] + cw[384 + threadIdx.x]);
+          p.col_part[(((size_t)b * p.H + h) * nqt + qt) * p.S + (j - p.lo)] = tsum;
+        }
+      }
+      // (no second barrier: the next head writes the other half of colw, and the barrier of head h+1 orders head h+2)
+    }
+    // acc tile: this CTA is the only writer of acc[b, rows of qt, columns of kt]; layers are separate launches
+    if (ri) {
+      float* dst = p.acc + ((size_t)b * p.S + (t - p.lo)) * p.S;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) {  // fully unrolled: acc[] must stay in registers
+        const int j = k0 + i;
+        if (j >= p.lo && j < hi && j < p.T) dst[j - p.lo] += acc[i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_s, TMEM_COLS);
+  }
+}
+
+inline cudaError_t launch_attention_probs_contact(const CUtensorMap& tmap_qkv, const ContactFuseParams& p,
+                                                  cudaStream_t stream) {
+  using namespace cfuse_cfg;
+  cudaError_t e = cudaFuncSetAttribute(attention_probs_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  dim3 grid((p.T + BLOCK - 1) / BLOCK, (p.T + BLOCK - 1) / BLOCK, p.B);
+  return launch_pdl(attention_probs_contact_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_qkv, p);
+}
+
+}  // namespace esmb200

@@ -216,7 +216,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 def run_stack(layers: Sequence, x: torch.Tensor, padding_mask: Optional[torch.Tensor],
               rope_cos: torch.Tensor, rope_sin: torch.Tensor, repr_out: Optional[Dict[int, torch.Tensor]],
-              attn_layers: Sequence[int], zero_pad_rows: bool = False):
+              attn_layers: Sequence[int], zero_pad_rows: bool = False, contact_job=None):
     """esmb200_stack_forward on x fp32 (B,T,E) in place. repr_out: {layer index (0-based): (B,T,E) tensor to fill}.
     Returns {layer index: (B,H,T,T) fp32} for the indices in attn_layers."""
     if not x.is_cuda:
@@ -255,6 +255,7 @@ def run_stack(layers: Sequence, x: torch.Tensor, padding_mask: Optional[torch.Te
                                              reprs if repr_out else None, attns if attn_layers else None,
                                              (len(attn_layers) * H * T * T) if attn_layers else 0,
                                              1 if zero_pad_rows else 0,
+                                             ctypes.byref(contact_job) if contact_job is not None else None,
                                              _ptr(ws), ws.numel(), _stream()))
     if stacked is not None:
         attn_t["stacked"] = stacked
@@ -406,13 +407,48 @@ class ContactPredictionHead(nn.Module):
                     ctypes.c_void_p(wl.data_ptr() + l * H * 4), _ptr(keep8), _ptr(acc), _ptr(row), _ptr(col),
                     B, H, T, lo, hi, _stream()))
                 torch.add(row, col.sum(2), out=a1[:, l])               # a1_c = rowsum + colsum, fixed summation order
-            a1f = a1.view(B, L * H, S)
+        return self._finalize(acc, a1.view(B, L * H, S), wl)
+
+    def _finalize(self, acc: torch.Tensor, a1f: torch.Tensor, wl: torch.Tensor) -> torch.Tensor:
+        """acc [B,S,S], a1f [B,L*H,S] (rowsum + colsum per channel), wl [L,H] -> contacts [B,S,S]."""
+        lib = _lib.load()
+        B, C, S = a1f.shape
+        with torch.cuda.device(acc.device):
+            a1f = a1f.contiguous()
             a12 = a1f.sum(-1, keepdim=True)                               # [B, L*H, 1]
-            u = (a1f * (wl.reshape(1, L * H, 1) / a12)).contiguous()
+            u = (a1f * (wl.reshape(1, C, 1) / a12)).contiguous()
             bias = _f32(self.regression.bias) if self.regression.bias is not None else None
-            out = torch.empty((B, S, S), dtype=torch.float32, device=dev)
-            _lib.check(lib.esmb200_contact_finalize(_ptr(acc), _ptr(u), _ptr(a1f), _ptr(bias), _ptr(out), B, L * H, S, _stream()))
+            out = torch.empty((B, S, S), dtype=torch.float32, device=acc.device)
+            _lib.check(lib.esmb200_contact_finalize(_ptr(acc), _ptr(u), _ptr(a1f), _ptr(bias), _ptr(out), B, C, S, _stream()))
         return out
+
+    # ---- fused path: the accumulators are filled by esmb200_stack_forward while the probabilities are written -------
+    def begin_job(self, tokens: torch.Tensor, num_layers: int, num_heads: int):
+        """Buffers + esmb200_contact_job for a [B,T] batch (attention_contact.cuh); finish_job() turns them into contacts."""
+        B, T = tokens.shape
+        lo = 1 if self.prepend_bos else 0
+        hi = T - 1 if self.append_eos else T
+        S = hi - lo
+        dev = tokens.device
+        nt = (T + 127) // 128
+        st = {
+            "keep": tokens.ne(self.eos_idx).to(torch.uint8).contiguous() if self.append_eos else None,
+            "acc": torch.zeros((B, S, S), dtype=torch.float32, device=dev),
+            "row": torch.empty((num_layers, B, num_heads, nt, S), dtype=torch.float32, device=dev),
+            "col": torch.empty((num_layers, B, num_heads, nt, S), dtype=torch.float32, device=dev),
+            "w": _f32(self.regression.weight).view(num_layers, num_heads).contiguous(),
+        }
+        job = _lib.ContactJob()
+        job.weights, job.keep = st["w"].data_ptr(), (st["keep"].data_ptr() if st["keep"] is not None else None)
+        job.acc, job.row_part, job.col_part = st["acc"].data_ptr(), st["row"].data_ptr(), st["col"].data_ptr()
+        job.lo, job.hi = lo, hi
+        st["job"] = job
+        return st
+
+    def finish_job(self, st) -> torch.Tensor:
+        L, B, H, nt, S = st["row"].shape
+        a1 = st["row"].sum(3) + st["col"].sum(3)                          # [L,B,H,S], fixed summation order
+        return self._finalize(st["acc"], a1.permute(1, 0, 2, 3).reshape(B, L * H, S), st["w"])
 
     def _forward_torch(self, tokens, attentions, w, lo, hi):
         """The same formula with PyTorch ops (non-CUDA or non-fp32 inputs; cross-check in the tests)."""
@@ -543,8 +579,12 @@ class ESM2(nn.Module):
             # esm2.py:111-121 layer loop (intermediate representations are copied out by the library)
             repr_out = {i - 1: torch.empty_like(x) for i in repr_layers if 0 < i < N}
             cos, sin = self._rope_tables(T)
+            # contacts: folded into the probability pass (fp16 mode; fp32x3 runs the separate kernels afterwards)
+            cjob = (self.contact_head.begin_job(tokens, N, self.attention_heads)
+                    if return_contacts and self.precision == "fp16" else None)
             attn_t = run_stack(list(self.layers), x, mask, cos, sin, repr_out,
-                               list(range(N)) if need_head_weights else [], zero_pad_rows=True)
+                               list(range(N)) if need_head_weights else [], zero_pad_rows=True,
+                               contact_job=cjob["job"] if cjob else None)
             for i, t in repr_out.items():
                 hidden[i + 1] = cast(t)
             # esm2.py:129 LM head, from the pre-LN stream (its first step is the same emb_layer_norm_after)
@@ -563,7 +603,8 @@ class ESM2(nn.Module):
             attentions = attn_t["stacked"]
             result["attentions"] = cast(attentions)
             if return_contacts:
-                result["contacts"] = cast(self.contact_head(tokens, attentions))
+                contacts = self.contact_head.finish_job(cjob) if cjob else self.contact_head(tokens, attentions)
+                result["contacts"] = cast(contacts)
         return result
 
     def predict_contacts(self, tokens):

@@ -95,6 +95,19 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
                           const float* rope_cos, const float* rope_sin, float* attn_probs, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Optional contact-head accumulation fused into the need_head_weights pass of esmb200_stack_forward
+ * (ContactPredictionHead.forward esm/modules.py:338-357, restated as in esmb200_contact_accumulate): every layer's
+ * probabilities are folded into the accumulators while they are written, the stacked attention tensor is never read
+ * back. S = hi - lo, nt = ceil(T / 128). Ignored (the separate probability kernel runs) for fp32x3 layers. */
+typedef struct esmb200_contact_job {
+  const float* weights; /* [n_layers, H] fp32: contact_head.regression.weight */
+  const uint8_t* keep;  /* [B,T] 1 = not <eos>, or NULL */
+  float* acc;           /* [B,S,S]  += sum_{l,h} w[l,h] A_{l,h}; zeroed by the caller */
+  float* row_part;      /* [n_layers,B,H,nt,S] row sums of A_{l,h} per 128-key tile (sum over nt = rowsum) */
+  float* col_part;      /* [n_layers,B,H,nt,S] column sums per 128-query tile (sum over nt = colsum) */
+  int32_t lo, hi;       /* cropped positions [lo,hi): 1 .. T-1 for <cls> ... <eos> */
+} esmb200_contact_job;
+
 /* The layer loop of ESM2.forward (esm2.py:111-121): runs n_layers layers in place on x.
  *   repr_out[i]  NULL or fp32 [B,T,E]: copy of x after layer i (hidden_representations[i+1], esm2.py:117-118)
  *   attn_out[i]  NULL or fp32 [B,H,T,T]: attention probabilities of layer i (esm2.py:119-121); batch b starts at
@@ -106,7 +119,8 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
 int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float* x, const uint8_t* pad_mask,
                           int32_t B, int32_t T, const float* rope_cos, const float* rope_sin,
                           float* const* repr_out, float* const* attn_out, int64_t attn_batch_stride,
-                          int32_t attn_flags, void* workspace, size_t workspace_bytes, void* stream);
+                          int32_t attn_flags, const esmb200_contact_job* contact /* nullable */, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Embedding prologue of ESM2.forward (esm2.py:84-95): gather from table [V,E], zero <mask> rows and rescale by
  * 0.88/(1 - n_mask/n_nonpad) when token_dropout, zero pad rows. tokens int64 [B,T] -> x fp32 [B,T,E]. */
