@@ -52,6 +52,74 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
 
 // (a variant writing fp16 rows straight from registers to global memory, without smem staging, measured slower:
 // profiles/r01_epilogue_experiments.txt)
+// cp.async.bulk.wait_group takes an immediate: at most n (0..4) of this thread's bulk groups may still be pending
+__device__ __forceinline__ void tma_store_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+  }
+}
+
+// LayerNorm of one fp32 row (read from L2, bypassing L1: it was just written by other SMs' reduce-adds) by one warp,
+// fp16 output (or hi | lo).  Same arithmetic as layernorm_rows_kernel (elementwise.cuh): row in registers, two passes.
+template <int MAXV>
+__device__ __noinline__ void warp_layernorm_row(const float* __restrict__ xrow, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, __half* __restrict__ orow, int E,
+                                                   float eps, int split, uint32_t lane) {
+  const int nvec = E / 4;
+  const float4* xr = reinterpret_cast<const float4*>(xrow);
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = (int)lane + i * 32;
+    if (idx < nvec) {
+      v[i] = __ldcg(xr + idx);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = (int)lane + i * 32;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = (int)lane + i * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+      uint2 h;
+      h.x = *reinterpret_cast<const uint32_t*>(&h01);
+      h.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(orow)[idx] = h;
+      if (split) {
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        uint2 l;
+        l.x = pack_half2(o.x - f01.x, o.y - f01.y);
+        l.y = pack_half2(o.z - f23.x, o.w - f23.y);
+        reinterpret_cast<uint2*>(orow + E)[idx] = l;
+      }
+    }
+  }
+}
+
 // SPLIT ("fp32x3" precision): both operands are stored as fp16 hi | lo halves along K (A [M,2K], B [N,2K]); the K loop
 // runs hi*hi + lo*hi + hi*lo (three passes over the same fp32 accumulator: 22 significand bits per operand, the
 // dropped lo*lo term is 2^-22 relative), and fp16 outputs are written as hi | lo pairs as well (lo part p.lo_col_off
@@ -72,6 +140,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * STAGES;                // [ACC_STAGES] one per CTA
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] used in the leader CTA only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  int* ln_todo = reinterpret_cast<int*>(tmem_slot + 2);  // [2] fused LayerNorm: slabs this CTA has to normalise (-1 = none)
 
   const uint32_t warp = threadIdx.x / 32;
   const uint32_t lane = threadIdx.x % 32;
@@ -120,6 +189,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 2) {
     tmem_alloc_pair(tmem_slot, TMEM_COLS);
     tmem_relinquish_pair();
+  }
+  if (warp == 3 && lane == 0) {
+    ln_todo[0] = -1;
+    ln_todo[1] = -1;
   }
   tc_fence_before();
   cluster_sync_all();
@@ -189,11 +262,48 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int iter = 0;
     [[maybe_unused]] float rc[32], rs[32];  // EPI_QKV_ROPE: cos / sin of this thread's row
     [[maybe_unused]] int rope_blk = -1;
+    // EPI_BIAS_RESIDUAL + fused LayerNorm (p.ln_counter): the slab of the previous tile, whose reduce-adds are retired
+    // one tile later (they have had a whole tile to complete, so the wait does not stall)
+    [[maybe_unused]] int ln_prev_blk = -1;
+    [[maybe_unused]] const bool fuse_ln = (EPI == EPI_BIAS_RESIDUAL) && p.ln_counter != nullptr;
+    [[maybe_unused]] const int ln_target = 4 * tiles_n;  // 2 CTAs x 2 column halves arrive once per column tile
+    // retire the reduce-adds of slab `blk` (at most `pending` younger bulk groups stay in flight), count the arrival and,
+    // as the last arriver, queue the slab for normalisation by this CTA
+    auto ln_arrive = [&](int blk, int pending) {
+      tma_store_wait_pending(pending);
+      __threadfence();
+      const int old = atomicAdd(p.ln_counter + blk, 1);
+      if (old == ln_target - 1) {
+        p.ln_counter[blk] = 0;  // ready for the next launch (stream-ordered after this kernel)
+        __threadfence();
+        ln_todo[chalf] = blk;
+      }
+    };
+    // all 8 epilogue warps: normalise the slabs queued by this CTA's two issuers
+    auto ln_service = [&]() {
+      named_bar_sync(3, 256);
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const int blk = ln_todo[q];
+        if (blk < 0) continue;  // uniform over the CTA
+        const int r0 = blk * PAIR_M + (int)ew * 32;
+        for (int r = 0; r < 32; ++r) {
+          const int rr = r0 + r;
+          if (rr >= p.M) break;
+          const float* xrow = reinterpret_cast<const float*>(p.out) + (size_t)rr * p.ldo;
+          __half* orow = reinterpret_cast<__half*>(p.ln_out) + (size_t)rr * (p.ln_split ? 2 : 1) * p.N;
+          warp_layernorm_row<20>(xrow, p.ln_gamma, p.ln_beta, orow, p.N, p.ln_eps, p.ln_split, lane);
+        }
+      }
+      named_bar_sync(3, 256);
+      if (issuer) ln_todo[chalf] = -1;
+    };
     for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
       const int row0 = m_blk * PAIR_M + rank * BLOCK_M;
       const int row = row0 + row_local;
+      [[maybe_unused]] int ln_groups = 0;  // bulk groups this issuer commits for this tile (fused LayerNorm)
       if constexpr (EPI == EPI_QKV_ROPE) {  // before the wait: the loads fly while the tile is still being multiplied
       // cos/sin of this thread's token position, 64 registers, reloaded only when the 256-row slab changes (tiles are
       // walked n-fastest, so once per tiles_n tiles) — r01 re-read them from L2 for every 64-column head group
@@ -518,6 +628,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if constexpr (EPI == EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmap_out, stg, col, row0);
             else tma_store_2d(&tmap_out, stg, col, row0);
             tma_store_commit();
+            ++ln_groups;
           }
           ++store_iter;
         }
@@ -526,8 +637,23 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
+      if constexpr (EPI == EPI_BIAS_RESIDUAL) {
+        if (fuse_ln) {  // after the accumulator stage has been handed back: the mainloop runs on underneath
+          if (issuer) {
+            if (ln_prev_blk >= 0) ln_arrive(ln_prev_blk, ln_groups);
+            ln_prev_blk = m_blk;
+          }
+          ln_service();
+        }
+      }
     }
     if (issuer) tma_store_wait_all();
+    if constexpr (EPI == EPI_BIAS_RESIDUAL) {
+      if (fuse_ln) {  // the last tile of this cluster: everything is complete now
+        if (issuer && ln_prev_blk >= 0) ln_arrive(ln_prev_blk, 0);
+        ln_service();
+      }
+    }
   }
 
   tc_fence_before();

@@ -254,6 +254,7 @@ int esmb200_attention_split(const void* qkv, const uint8_t* pad_mask, void* ctx,
  * "attn"      8 (default: attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, 2 CTAs/SM)          env ESMB200_ATTN
  * "attn_poly" 0 | 2 | 3 | 4 (default): every n-th pair of softmax exponentials on the FMA pipe   env ESMB200_ATTN_POLY
  * "pdl"       0 (default) | 1: programmatic dependent launch between the layer's kernels        env ESMB200_PDL
+ * "fuse_ln"   1 (default) | 0: LayerNorm in the tail of the residual GEMMs instead of separate kernels    env ESMB200_FUSE_LN
  * Returns ESMB200_EINVAL for an unknown name or value. Not thread-safe against concurrent launches. */
 int esmb200_set_option(const char* name, int32_t value);
 
