@@ -181,6 +181,14 @@ int fuse_ln() {
   return g_fuse_ln;
 }
 
+int ln_debug() {
+  static const int v = [] {
+    const char* e = getenv("ESMB200_LN_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 constexpr int kMaxDevices = 64;
 
 int num_sms() {  // per device: one process may drive several GPUs
@@ -588,7 +596,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   g.M = M; g.N = E; g.K = Ea; g.bias = L->out_b; g.out = x; g.ldo = E;
   if (fuse) {  // LN2 (modules.py:137) in the tail of this GEMM: xn is free (the QKV GEMM that read it has completed)
     g.ln_gamma = L->ln2_w; g.ln_beta = L->ln2_b; g.ln_eps = L->eps; g.ln_out = ws.xn; g.ln_split = split;
-    g.ln_counter = ws.ln_counter;
+    g.ln_counter = ws.ln_counter; g.ln_debug = ln_debug();
   }
   rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT, split);
   if (rc) return rc;
@@ -609,7 +617,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
   if (fuse && next) {  // LN1 of the next layer (modules.py:124) in the tail of fc2: fc1, which read xn, has completed
     g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_eps = next->eps; g.ln_out = ws.xn; g.ln_split = split;
-    g.ln_counter = ws.ln_counter;
+    g.ln_counter = ws.ln_counter; g.ln_debug = ln_debug();
   }
   rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2, split);
   return rc;

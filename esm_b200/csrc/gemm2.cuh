@@ -270,17 +270,19 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // retire the reduce-adds of slab `blk` (at most `pending` younger bulk groups stay in flight), count the arrival and,
     // as the last arriver, queue the slab for normalisation by this CTA
     auto ln_arrive = [&](int blk, int pending) {
-      tma_store_wait_pending(pending);
-      __threadfence();
+      if (!(p.ln_debug & 1)) tma_store_wait_pending(pending);
+      if (p.ln_debug & 4) return;
+      if (!(p.ln_debug & 2)) __threadfence();
       const int old = atomicAdd(p.ln_counter + blk, 1);
       if (old == ln_target - 1) {
         p.ln_counter[blk] = 0;  // ready for the next launch (stream-ordered after this kernel)
-        __threadfence();
+        if (!(p.ln_debug & 2)) __threadfence();
         ln_todo[chalf] = blk;
       }
     };
     // all 8 epilogue warps: normalise the slabs queued by this CTA's two issuers
     auto ln_service = [&]() {
+      if (p.ln_debug & 8) return;
       named_bar_sync(3, 256);
 #pragma unroll 1
       for (int q = 0; q < 2; ++q) {

@@ -42,6 +42,7 @@ struct GemmParams {
   void* ln_out;           // fp16 [M, N], or [M, 2N] hi | lo when ln_split
   int ln_split;
   int* ln_counter;        // [ceil(M/256)] arrival counters, zero before the first launch; the last arriver resets its slab
+  int ln_debug;           // developer bits (ESMB200_LN_DEBUG): 1 skip the bulk wait, 2 skip fences, 4 skip arrivals, 8 skip service
 };
 
 
