@@ -677,7 +677,7 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
       const int S = contact->hi - contact->lo;
       const size_t part = (size_t)B * H * nt128 * S;
       cl.w = contact->weights + (size_t)i * H; cl.keep = contact->keep; cl.acc = contact->acc;
-      cl.row_part = contact->row_part + (size_t)i * part; cl.col_part = contact->col_part + (size_t)i * part;
+      cl.row_part = contact->row_part + (size_t)i * 4 * part; cl.col_part = contact->col_part + (size_t)i * part;
       cl.lo = contact->lo; cl.S = S;
     }
     // a repr_out copy of x after layer i does not disturb the fusion: fc2's LayerNorm of layer i+1 reads x, the copy too

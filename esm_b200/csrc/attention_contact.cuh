@@ -7,14 +7,18 @@
 // ContactPredictionHead.forward, /root/reference/esm/modules.py:338-357 (eos masking, bos/eos crop, symmetrize :27-29,
 // apc :32-41), in the restated form of elementwise.cuh: with A_h the masked, cropped map of head h,
 //     acc[b,i,j]        += sum_h w_h A_h[i,j]                  (one owner CTA per tile: plain read-modify-write)
-//     row_part[b,h,kt,i] = sum_{j in key tile kt} A_h[i,j]     (partials over the key tiles, summed by the caller)
+//     row_part[b,h,4kt+c,i] = sum_{j in 32-key quarter c of key tile kt} A_h[i,j]   (partials, summed by the caller)
 //     col_part[b,h,qt,j] = sum_{i in query tile qt} A_h[i,j]   (partials over the query tiles)
 // No atomics: every output element has one writer and every sum a fixed order -> bit-reproducible contacts.
 //
-// One CTA = (128-key tile, 128-query tile, sequence) and LOOPS OVER THE HEADS: warp 4 lane 0 streams (Q_h, K_h) tiles
+// One CTA = (128-key tile, 128-query tile, sequence) and LOOPS OVER THE HEADS: warp 8 lane 0 streams (Q_h, K_h) tiles
 // through a 2-stage TMA ring and issues S_h = Q_h K_h^T (4 x UMMA 128x128x16) into a double-buffered TMEM accumulator;
-// warps 0-3 (thread = query row) turn S_h into p = exp(s - m) / l with the statistics saved by the forward kernel, write
-// the tile through a padded shared-memory transpose (every global store is a 128-byte row segment) and accumulate.
+// warps 0-15 (thread = query row x 32-key quarter: warps w, w+4, w+8, w+12 share the TMEM lanes of rows 32(w%4)..) turn
+// S_h into p = exp(s - m) / l with the statistics saved by the forward kernel, write the tile through a padded
+// shared-memory transpose (every global store is a 128-byte row segment) and accumulate.  A warp's loop is a latency
+// chain (TMEM load -> 32 exponentials -> transpose -> 32 row stores): the first version (4 compute warps, 2 CTAs/SM,
+// 128 accumulators per thread) ran at 22 K cycles per head with every unit idle (profiles/r02_ncu_contact_fused.txt);
+// sixteen compute warps with 32 accumulators each keep four warps per scheduler busy.
 #pragma once
 
 #include "attention_common.cuh"
@@ -35,22 +39,22 @@ struct ContactFuseParams {
   const float* w;            // [H] regression weights of this layer's heads
   const uint8_t* keep;       // [B,T] 1 = not <eos>, or NULL
   float* acc;                // [B,S,S]
-  float* row_part;           // [B,H,nkt,S]
+  float* row_part;           // [B,H,4*nkt,S]
   float* col_part;           // [B,H,nqt,S]
   int lo, S;                 // cropped positions [lo, lo+S)
 };
 
 namespace cfuse_cfg {
 constexpr int BLOCK = 128;            // query rows and keys per tile
-constexpr int NUM_THREADS = 160;      // warps 0-3: one thread per query row; warp 4: TMA + MMA issuer
+constexpr int NUM_THREADS = 544;      // warps 0-15: thread = (query row, 32-key quarter); warp 16: TMA + MMA issuer
 constexpr int STAGES = 2;
 constexpr int TILE_BYTES = attn_cfg::TILE_BYTES;
 constexpr int TMEM_COLS = 256;        // S double buffer
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 4 * 32 * 33 * 4 /*transpose*/ +
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 16 * 32 * 33 * 4 /*transpose*/ +
                            2 * 4 * 128 * 4 /*column partials, double buffered*/ + 128 * 4 /*row keep flags*/;
 }  // namespace cfuse_cfg
 
-__global__ void __launch_bounds__(cfuse_cfg::NUM_THREADS, 2)
+__global__ void __launch_bounds__(cfuse_cfg::NUM_THREADS, 1)
 attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const ContactFuseParams p) {
   using namespace cfuse_cfg;
   constexpr float LOG2E = attn_cfg::LOG2E;
@@ -64,8 +68,8 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
   uint64_t* s_full = bars + 4;   // [2] MMA -> softmax
   uint64_t* s_free = bars + 6;   // [2] softmax -> MMA (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * TILE_BYTES + 128);  // [4][32*33]
-  float* colw = tiles + 4 * 32 * 33;                                              // [2][4][128]
+  float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * TILE_BYTES + 128);  // [16][32*33]
+  float* colw = tiles + 16 * 32 * 33;                                             // [2][4][128]
   float* rowkeep = colw + 2 * 4 * 128;                                            // [128]
 
   const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -79,11 +83,11 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 128);
+      mbar_init(&s_free[i], 512);
     }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 16) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -95,7 +99,7 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
   const uint32_t tmem_s = *tmem_slot;
   const bool live = k0 < p.kvlen[b];  // otherwise every key of this tile is masked: all probabilities are exactly 0
 
-  if (warp == 4) {
+  if (warp == 16) {
     // ===================== TMA producer + MMA issuer =====================
     if (lane == 0 && live) {
       constexpr uint32_t idesc = umma_idesc_f16(128, 128, false);
@@ -126,96 +130,86 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
       }
     }
   } else {
-    // ===================== probabilities + contact accumulation: one thread per query row =====================
-    const uint32_t lane_addr = (warp * 32u) << 16;
-    const int t = q0 + (int)threadIdx.x;          // this thread's query position
+    // ===================== probabilities + contact accumulation: thread = (query row, 32-key quarter) =====================
+    const uint32_t rq = warp & 3;                 // row quarter: TMEM lanes 32*rq ..
+    const uint32_t cq = warp >> 2;                // key quarter: columns [32*cq, 32*cq + 32) of the tile
+    const uint32_t lane_addr = (rq * 32u) << 16;
+    const int trow = (int)(rq * 32 + lane);       // row of the tile
+    const int t = q0 + trow;                      // this thread's query position
     const bool row_ok = t < p.T;
     const int ncols = min(BLOCK, p.T - k0);
     const int hi = p.lo + p.S;
     const uint8_t* kp = p.keep ? p.keep + (size_t)b * p.T : nullptr;
     // contact masks: position kept (not <eos>) and inside the bos/eos crop
     const bool ri = row_ok && t >= p.lo && t < hi && (!kp || kp[t]);
-    rowkeep[threadIdx.x] = ri ? 1.f : 0.f;
-    uint32_t cmask[4], kw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int j = k0 + c * 32 + (int)lane;
-      const bool kj = j < p.T && j >= p.lo && j < hi && (!kp || kp[j]);
-      cmask[c] = __ballot_sync(0xffffffffu, kj);
-    }
-    if (live) {
-      const uint4 kw4 = __ldg(reinterpret_cast<const uint4*>(p.keybits + (size_t)b * p.words + kt * 4));
-      kw[0] = kw4.x; kw[1] = kw4.y; kw[2] = kw4.z; kw[3] = kw4.w;
-    }
+    if (cq == 0) rowkeep[trow] = ri ? 1.f : 0.f;
+    const int jlane = k0 + (int)cq * 32 + (int)lane;
+    const uint32_t cm = __ballot_sync(0xffffffffu, jlane < p.T && jlane >= p.lo && jlane < hi && (!kp || kp[jlane]));
+    const uint32_t wd = live ? __ldg(p.keybits + (size_t)b * p.words + kt * 4 + cq) : 0u;
     const bool qpad = p.zero_pad_rows && row_ok && !((p.keybits[(size_t)b * p.words + (t >> 5)] >> (t & 31)) & 1u);
-    named_bar_sync(1, 128);  // rowkeep visible to the four warps
+    named_bar_sync(1, 512);  // rowkeep visible
     float* tile = tiles + warp * (32 * 33);
-    const int t_warp0 = q0 + (int)warp * 32;
+    const int t_warp0 = q0 + (int)rq * 32;
     const int nrows = min(32, p.T - t_warp0);
-    float acc[128];
+    const bool cols_ok = (int)cq * 32 < ncols;    // uniform over the warp
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 
     for (int h = 0; h < p.H; ++h) {
       const int s = h & 1;
       const float wh = __ldg(p.w + h);
-      float mneg = 0.f, inv = 0.f;
+      float rs = 0.f, cs = 0.f;
       if (live) {
         const size_t si = ((size_t)b * p.H + h) * p.T + (row_ok ? t : 0);
-        mneg = -p.row_max[si] * LOG2E;
+        const float mneg = -p.row_max[si] * LOG2E;
         const float l = p.row_sum[si];
-        inv = (l > 0.f && !qpad) ? 1.0f / l : 0.f;  // esm2.py:135-139: rows of padded query tokens are zero
+        const float inv = (l > 0.f && !qpad) ? 1.0f / l : 0.f;  // esm2.py:135-139: rows of padded query tokens are zero
         mbar_wait(&s_full[s], (h >> 1) & 1);
         tc_fence_after();
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + s * 128 + cq * 32, sv);
+        tmem_wait_ld_dep(sv);
+        tc_fence_before();
+        mbar_arrive(&s_free[s]);  // S_h is in registers: the MMA of head h+2 may overwrite this buffer
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pr = ((wd >> i) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, mneg)) * inv : 0.f;
+          tile[lane * 33 + i] = pr;
+          const float x = (ri && ((cm >> i) & 1u)) ? pr : 0.f;
+          acc[i] = fmaf(wh, x, acc[i]);
+          rs += x;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = 0.f;
       }
-      float* base = p.probs + (size_t)b * p.batch_stride + (size_t)h * p.T * p.T + k0;
-      float rs = 0.f;
-      float colp[4];
+      __syncwarp();
+      if (cols_ok && (int)cq * 32 + (int)lane < ncols) {
+        float* dst = p.probs + (size_t)b * p.batch_stride + (size_t)h * p.T * p.T + (size_t)t_warp0 * p.T + k0 + cq * 32 + lane;
+        if (nrows == 32) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        colp[c] = 0.f;
-        if (c * 32 >= ncols) continue;  // uniform
-        if (live) {
-          uint32_t sv[32];
-          tmem_ld_32x32b_x32(tmem_s + lane_addr + s * 128 + c * 32, sv);
-          tmem_wait_ld_dep(sv);
-          const uint32_t wd = kw[c], cm = cmask[c];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float pr = ((wd >> i) & 1u) ? ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, mneg)) * inv : 0.f;
-            tile[lane * 33 + i] = pr;
-            const float x = (ri && ((cm >> i) & 1u)) ? pr : 0.f;
-            acc[c * 32 + i] = fmaf(wh, x, acc[c * 32 + i]);
-            rs += x;
+          for (int r = 0; r < 32; ++r) {  // 32 independent shared loads, then 32 row-segment stores
+            const float v = tile[r * 33 + lane];
+            dst[(size_t)r * p.T] = v;
+            cs = fmaf(v, rowkeep[rq * 32 + r], cs);
           }
         } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tile[lane * 33 + i] = 0.f;
-        }
-        __syncwarp();
-        const int col = c * 32 + (int)lane;
-        float cs = 0.f;
-        if (col < ncols) {
           for (int r = 0; r < nrows; ++r) {
             const float v = tile[r * 33 + lane];
-            base[(size_t)(t_warp0 + r) * p.T + col] = v;
-            cs = fmaf(v, rowkeep[warp * 32 + r], cs);
+            dst[(size_t)r * p.T] = v;
+            cs = fmaf(v, rowkeep[rq * 32 + r], cs);
           }
         }
-        colp[c] = ((cmask[c] >> lane) & 1u) ? cs : 0.f;
-        __syncwarp();
       }
-      if (live) {
-        tc_fence_before();
-        mbar_arrive(&s_free[s]);  // S_h has been read: the MMA of head h+2 may overwrite this buffer
-      }
-      // row partial of this key tile; column partials of this query tile (4 warps summed in a fixed order)
-      if (row_ok && t >= p.lo && t < hi) p.row_part[(((size_t)b * p.H + h) * nkt + kt) * p.S + (t - p.lo)] = rs;  // 0 for <eos>
+      __syncwarp();
+      // row partial of this 32-key quarter (4 * nkt partials per row); column partials of this query tile
+      if (row_ok && t >= p.lo && t < hi)
+        p.row_part[(((size_t)b * p.H + h) * (4 * nkt) + 4 * kt + cq) * p.S + (t - p.lo)] = rs;  // 0 for <eos>
       float* cw = colw + (h & 1) * (4 * 128);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) cw[warp * 128 + c * 32 + lane] = colp[c];
-      named_bar_sync(1, 128);
-      {
+      cw[rq * 128 + cq * 32 + lane] = ((cm >> lane) & 1u) ? cs : 0.f;
+      named_bar_sync(1, 512);
+      if (threadIdx.x < 128) {
         const int j = k0 + (int)threadIdx.x;
         if (j >= p.lo && j < hi && j < p.T) {
           const float tsum = (cw[threadIdx.x] + cw[128 + threadIdx.x]) + (cw[256 + threadIdx.x] + cw[384 + threadIdx.x]);
@@ -228,8 +222,8 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
     if (ri) {
       float* dst = p.acc + ((size_t)b * p.S + (t - p.lo)) * p.S;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) {  // fully unrolled: acc[] must stay in registers
-        const int j = k0 + i;
+      for (int i = 0; i < 32; ++i) {  // fully unrolled: acc[] must stay in registers
+        const int j = k0 + (int)cq * 32 + i;
         if (j >= p.lo && j < hi && j < p.T) dst[j - p.lo] += acc[i];
       }
     }
@@ -237,7 +231,7 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc(tmem_s, TMEM_COLS);
   }

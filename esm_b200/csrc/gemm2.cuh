@@ -79,7 +79,15 @@ __device__ __forceinline__ void warp_layernorm_rows(const float* __restrict__ x0
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {  // unconditional definition (clamped address) so that v[][] lives in registers:
       const int idx = (int)lane + i * 32;  // a guarded one made ptxas keep the array on the local-memory stack
-      const float4 t = __ldcg(xr + (idx < nvec ? idx : 0));
+      // weak load that does not allocate in L1 (LDG.E.NA): the rows were written by other SMs' reduce-adds during this
+      // kernel, are read exactly once here, and no generic load of this kernel has touched their lines before (L1 is
+      // invalidated at launch), so L1 cannot hold a stale copy.  __ldcg compiles to LDG.STRONG.GPU on sm_100, which
+      // serialises: 17 us per row measured.
+      float4 t;
+      asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(xr + (idx < nvec ? idx : 0))
+                   : "memory");
       v[r][i] = idx < nvec ? t : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }

@@ -434,7 +434,7 @@ class ContactPredictionHead(nn.Module):
         st = {
             "keep": tokens.ne(self.eos_idx).to(torch.uint8).contiguous() if self.append_eos else None,
             "acc": torch.zeros((B, S, S), dtype=torch.float32, device=dev),
-            "row": torch.empty((num_layers, B, num_heads, nt, S), dtype=torch.float32, device=dev),
+            "row": torch.empty((num_layers, B, num_heads, 4 * nt, S), dtype=torch.float32, device=dev),
             "col": torch.empty((num_layers, B, num_heads, nt, S), dtype=torch.float32, device=dev),
             "w": _f32(self.regression.weight).view(num_layers, num_heads).contiguous(),
         }
@@ -446,7 +446,7 @@ class ContactPredictionHead(nn.Module):
         return st
 
     def finish_job(self, st) -> torch.Tensor:
-        L, B, H, nt, S = st["row"].shape
+        L, B, H, _, S = st["row"].shape
         a1 = st["row"].sum(3) + st["col"].sum(3)                          # [L,B,H,S], fixed summation order
         return self._finalize(st["acc"], a1.permute(1, 0, 2, 3).reshape(B, L * H, S), st["w"])
 

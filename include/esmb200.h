@@ -103,7 +103,7 @@ typedef struct esmb200_contact_job {
   const float* weights; /* [n_layers, H] fp32: contact_head.regression.weight */
   const uint8_t* keep;  /* [B,T] 1 = not <eos>, or NULL */
   float* acc;           /* [B,S,S]  += sum_{l,h} w[l,h] A_{l,h}; zeroed by the caller */
-  float* row_part;      /* [n_layers,B,H,nt,S] row sums of A_{l,h} per 128-key tile (sum over nt = rowsum) */
+  float* row_part;      /* [n_layers,B,H,4*nt,S] row sums of A_{l,h} per 32-key quarter tile (sum over 4*nt = rowsum) */
   float* col_part;      /* [n_layers,B,H,nt,S] column sums per 128-query tile (sum over nt = colsum) */
   int32_t lo, hi;       /* cropped positions [lo,hi): 1 .. T-1 for <cls> ... <eos> */
 } esmb200_contact_job;
