@@ -170,25 +170,6 @@ int qkv_chunked() {  // tile walk of the QKV GEMM (gemm2.cuh): 1 = one contiguou
   return v;
 }
 
-// LayerNorm fused into the tail of the residual GEMMs (gemm2.cuh, GemmParams::ln_counter).  -1: environment
-// ESMB200_FUSE_LN (default on); esmb200_set_option("fuse_ln", v) overrides
-int g_fuse_ln = -1;
-int fuse_ln() {
-  if (g_fuse_ln < 0) {
-    const char* e = getenv("ESMB200_FUSE_LN");
-    g_fuse_ln = (e && e[0] == '0') ? 0 : 1;
-  }
-  return g_fuse_ln;
-}
-
-int ln_debug() {
-  static const int v = [] {
-    const char* e = getenv("ESMB200_LN_DEBUG");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
-
 constexpr int kMaxDevices = 64;
 
 int num_sms() {  // per device: one process may drive several GPUs
@@ -526,7 +507,7 @@ size_t esmb200_workspace_bytes(int32_t E, int32_t H, int32_t F, int32_t B, int32
   const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2 * pf, 1024) + align_up(M * Ea * 2 * pf, 1024);
   const size_t big_h = align_up(M * F * 2 * pf, 1024);
   const size_t big = big_qkv_ctx > big_h ? big_qkv_ctx : big_h;    // h aliases qkv+ctx
-  return a + big + attn_scratch_bytes(B, T, H) + align_up(((M + 255) / 256) * sizeof(int), 256) + 1024;
+  return a + big + attn_scratch_bytes(B, T, H) + 1024;
 }
 
 namespace {
@@ -536,7 +517,6 @@ struct Workspace {
   __half* ctx;
   __half* h;
   AttnScratch as;
-  int* ln_counter;  // [ceil(M/256)] slab arrival counters of the fused LayerNorm (zero between launches)
 };
 
 int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, int F, int B, int T, int split) {
@@ -552,8 +532,6 @@ int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, 
   const size_t big_h = align_up(M * F * 2 * pf, 1024);
   p += big_qkv_ctx > big_h ? big_qkv_ctx : big_h;
   ws->as = carve_attn_scratch(p, B, T, H);
-  p += attn_scratch_bytes(B, T, H);
-  ws->ln_counter = reinterpret_cast<int*>(p);
   return ESMB200_OK;
 }
 
@@ -564,17 +542,13 @@ struct ActMaps {
 
 int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* rope_cos, const float* rope_sin,
                        float* attn_probs, long long attn_batch_stride, int attn_flags, const Workspace& ws,
-                       const ActMaps& am, cudaStream_t st, const ContactLayer* contact = nullptr,
-                       bool ln1_done = false, const esmb200_layer* next = nullptr) {
-  // ln1_done: the previous layer's fc2 epilogue already wrote LN1(x) of THIS layer into ws.xn;
-  // next: the layer whose LN1 this layer's fc2 epilogue should produce (NULL: none)
+                       const ActMaps& am, cudaStream_t st, const ContactLayer* contact = nullptr) {
   const int E = L->E, F = L->F, H = L->H, Ea = L->Ea;
   const int M = B * T;
   const bool split = L->split != 0;
-  const bool fuse = fuse_ln() && E % 4 == 0 && E <= 20 * 128;
   cudaError_t e = cudaSuccess;
   // LN1 -> fp16 (modules.py:124)
-  if (!ln1_done) {
+  {
     ProfScope ps(T_LN1, st);
     e = split ? launch_layernorm<2>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st)
               : launch_layernorm<1>(x, L->ln1_w, L->ln1_b, ws.xn, M, E, L->eps, st);
@@ -594,14 +568,10 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = Ea; g.bias = L->out_b; g.out = x; g.ldo = E;
-  if (fuse) {  // LN2 (modules.py:137) in the tail of this GEMM: xn is free (the QKV GEMM that read it has completed)
-    g.ln_gamma = L->ln2_w; g.ln_beta = L->ln2_b; g.ln_eps = L->eps; g.ln_out = ws.xn; g.ln_split = split;
-    g.ln_counter = ws.ln_counter; g.ln_debug = ln_debug();
-  }
   rc = launch_gemm(EPI_BIAS_RESIDUAL, am.ctx, L->tm_out, am.x_out, g, st, T_OUT, split);
   if (rc) return rc;
   // LN2 -> fp16 (modules.py:137)
-  if (!fuse) {
+  {
     ProfScope ps(T_LN2, st);
     e = split ? launch_layernorm<2>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st)
               : launch_layernorm<1>(x, L->ln2_w, L->ln2_b, ws.xn, M, E, L->eps, st);
@@ -615,10 +585,6 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   // fc2 + residual (modules.py:139-140)
   memset(&g, 0, sizeof g);
   g.M = M; g.N = E; g.K = F; g.bias = L->fc2_b; g.out = x; g.ldo = E;
-  if (fuse && next) {  // LN1 of the next layer (modules.py:124) in the tail of fc2: fc1, which read xn, has completed
-    g.ln_gamma = next->ln1_w; g.ln_beta = next->ln1_b; g.ln_eps = next->eps; g.ln_out = ws.xn; g.ln_split = split;
-    g.ln_counter = ws.ln_counter; g.ln_debug = ln_debug();
-  }
   rc = launch_gemm(EPI_BIAS_RESIDUAL, am.h, L->tm_fc2, am.x_out, g, st, T_FC2, split);
   return rc;
 }
@@ -668,8 +634,6 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
   if (rc) return rc;
   rc = run_key_bits(pad_mask, ws.as, B, T, st);
   if (rc) return rc;
-  const bool fuse = fuse_ln() && E % 4 == 0 && E <= 20 * 128;
-  if (fuse) CK(cudaMemsetAsync(ws.ln_counter, 0, (((size_t)B * T + 255) / 256) * sizeof(int), st));
   const int nt128 = (T + 127) / 128;
   for (int i = 0; i < n_layers; ++i) {
     ContactLayer cl;
@@ -677,13 +641,11 @@ int esmb200_stack_forward(esmb200_layer* const* layers, int32_t n_layers, float*
       const int S = contact->hi - contact->lo;
       const size_t part = (size_t)B * H * nt128 * S;
       cl.w = contact->weights + (size_t)i * H; cl.keep = contact->keep; cl.acc = contact->acc;
-      cl.row_part = contact->row_part + (size_t)i * 4 * part; cl.col_part = contact->col_part + (size_t)i * part;
+      cl.row_part = contact->row_part + (size_t)i * 4 * part; cl.col_part = contact->col_part + (size_t)i * 4 * part;
       cl.lo = contact->lo; cl.S = S;
     }
-    // a repr_out copy of x after layer i does not disturb the fusion: fc2's LayerNorm of layer i+1 reads x, the copy too
     rc = layer_forward_impl(layers[i], x, B, T, rope_cos, rope_sin, attn_out ? attn_out[i] : nullptr, attn_batch_stride,
-                            attn_flags, ws, am, st, contact ? &cl : nullptr, /*ln1_done=*/fuse && i > 0,
-                            /*next=*/(fuse && i + 1 < n_layers) ? layers[i + 1] : nullptr);
+                            attn_flags, ws, am, st, contact ? &cl : nullptr);
     if (rc) return rc;
     if (repr_out && repr_out[i])
       CK(cudaMemcpyAsync(repr_out[i], x, (size_t)B * T * E * 4, cudaMemcpyDeviceToDevice, st));
@@ -1144,7 +1106,6 @@ int esmb200_set_option(const char* name, int32_t value) {
     return ESMB200_OK;
   }
   if (!strcmp(name, "pdl") && (value == 0 || value == 1)) { pdl_flag() = value; return ESMB200_OK; }
-  if (!strcmp(name, "fuse_ln") && (value == 0 || value == 1)) { g_fuse_ln = value; return ESMB200_OK; }
   return fail(ESMB200_EINVAL, std::string("unknown option or value: ") + name);
 }
 

@@ -8,7 +8,7 @@
 // apc :32-41), in the restated form of elementwise.cuh: with A_h the masked, cropped map of head h,
 //     acc[b,i,j]        += sum_h w_h A_h[i,j]                  (one owner CTA per tile: plain read-modify-write)
 //     row_part[b,h,4kt+c,i] = sum_{j in 32-key quarter c of key tile kt} A_h[i,j]   (partials, summed by the caller)
-//     col_part[b,h,qt,j] = sum_{i in query tile qt} A_h[i,j]   (partials over the query tiles)
+//     col_part[b,h,4qt+r,j] = sum_{i in 32-row quarter r of query tile qt} A_h[i,j]   (partials, summed by the caller)
 // No atomics: every output element has one writer and every sum a fixed order -> bit-reproducible contacts.
 //
 // One CTA = (128-key tile, 128-query tile, sequence) and LOOPS OVER THE HEADS: warp 8 lane 0 streams (Q_h, K_h) tiles
@@ -40,7 +40,7 @@ struct ContactFuseParams {
   const uint8_t* keep;       // [B,T] 1 = not <eos>, or NULL
   float* acc;                // [B,S,S]
   float* row_part;           // [B,H,4*nkt,S]
-  float* col_part;           // [B,H,nqt,S]
+  float* col_part;           // [B,H,4*nqt,S]
   int lo, S;                 // cropped positions [lo, lo+S)
 };
 
@@ -51,7 +51,7 @@ constexpr int STAGES = 2;
 constexpr int TILE_BYTES = attn_cfg::TILE_BYTES;
 constexpr int TMEM_COLS = 256;        // S double buffer
 constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 16 * 32 * 33 * 4 /*transpose*/ +
-                           2 * 4 * 128 * 4 /*column partials, double buffered*/ + 128 * 4 /*row keep flags*/;
+                           128 * 4 /*row keep flags*/;
 }  // namespace cfuse_cfg
 
 __global__ void __launch_bounds__(cfuse_cfg::NUM_THREADS, 1)
@@ -69,8 +69,7 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
   uint64_t* s_free = bars + 6;   // [2] softmax -> MMA (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * TILE_BYTES + 128);  // [16][32*33]
-  float* colw = tiles + 16 * 32 * 33;                                             // [2][4][128]
-  float* rowkeep = colw + 2 * 4 * 128;                                            // [128]
+  float* rowkeep = tiles + 16 * 32 * 33;                                          // [128]
 
   const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int kt = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
@@ -206,17 +205,10 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
       // row partial of this 32-key quarter (4 * nkt partials per row); column partials of this query tile
       if (row_ok && t >= p.lo && t < hi)
         p.row_part[(((size_t)b * p.H + h) * (4 * nkt) + 4 * kt + cq) * p.S + (t - p.lo)] = rs;  // 0 for <eos>
-      float* cw = colw + (h & 1) * (4 * 128);
-      cw[rq * 128 + cq * 32 + lane] = ((cm >> lane) & 1u) ? cs : 0.f;
-      named_bar_sync(1, 512);
-      if (threadIdx.x < 128) {
-        const int j = k0 + (int)threadIdx.x;
-        if (j >= p.lo && j < hi && j < p.T) {
-          const float tsum = (cw[threadIdx.x] + cw[128 + threadIdx.x]) + (cw[256 + threadIdx.x] + cw[384 + threadIdx.x]);
-          p.col_part[(((size_t)b * p.H + h) * nqt + qt) * p.S + (j - p.lo)] = tsum;
-        }
-      }
-      // (no second barrier: the next head writes the other half of colw, and the barrier of head h+1 orders head h+2)
+      // column partial of this warp's 32 rows x 32 columns (4 * nqt partials per column): no cross-warp reduction, so the
+      // sixteen warps never meet at a barrier inside the head loop and overlap each other's TMEM / MUFU / store phases
+      if (jlane >= p.lo && jlane < hi && jlane < p.T)
+        p.col_part[(((size_t)b * p.H + h) * (4 * nqt) + 4 * qt + rq) * p.S + (jlane - p.lo)] = ((cm >> lane) & 1u) ? cs : 0.f;
     }
     // acc tile: this CTA is the only writer of acc[b, rows of qt, columns of kt]; layers are separate launches
     if (ri) {

@@ -52,100 +52,6 @@ __device__ __forceinline__ void stage_row_sw128(uint8_t* stg, uint32_t row, cons
 
 // (a variant writing fp16 rows straight from registers to global memory, without smem staging, measured slower:
 // profiles/r01_epilogue_experiments.txt)
-// cp.async.bulk.wait_group takes an immediate: at most n (0..4) of this thread's bulk groups may still be pending
-__device__ __forceinline__ void tma_store_wait_pending(int n) {
-  switch (n) {
-    case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
-    default: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
-  }
-}
-
-// LayerNorm of R fp32 rows (read from L2, bypassing L1: they were just written by other SMs' reduce-adds) by one warp,
-// fp16 output (or hi | lo).  Same arithmetic as layernorm_rows_kernel (elementwise.cuh): rows in registers, two passes —
-// bit-identical results.  R = 2 keeps the loads of two rows in flight (the loop is latency-bound on the L2 round trip).
-template <int MAXV, int R>
-__device__ __forceinline__ void warp_layernorm_rows(const float* __restrict__ x0, size_t x_pitch,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    __half* __restrict__ o0, size_t o_pitch, int E, float eps, int split,
-                                                    uint32_t lane) {
-  const int nvec = E / 4;
-  float4 v[R][MAXV];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const float4* xr = reinterpret_cast<const float4*>(x0 + r * x_pitch);
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {  // unconditional definition (clamped address) so that v[][] lives in registers:
-      const int idx = (int)lane + i * 32;  // a guarded one made ptxas keep the array on the local-memory stack
-      // weak load that does not allocate in L1 (LDG.E.NA): the rows were written by other SMs' reduce-adds during this
-      // kernel, are read exactly once here, and no generic load of this kernel has touched their lines before (L1 is
-      // invalidated at launch), so L1 cannot hold a stale copy.  __ldcg compiles to LDG.STRONG.GPU on sm_100, which
-      // serialises: 17 us per row measured.
-      float4 t;
-      asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                   : "l"(xr + (idx < nvec ? idx : 0))
-                   : "memory");
-      v[r][i] = idx < nvec ? t : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  float mean[R], rstd[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int idx = (int)lane + i * 32;
-      if (idx < nvec) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    }
-    mean[r] = warp_sum(s) / (float)E;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int idx = (int)lane + i * 32;
-      if (idx < nvec) {
-        const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
-        q += (a * a + b * b) + (c * c + d * d);
-      }
-    }
-    rstd[r] = rsqrtf(warp_sum(q) / (float)E + eps);
-  }
-  // chunk-major: gamma / beta of one chunk are loaded once and used for every row, so they never occupy more than 8
-  // registers (row-major order let the compiler hoist all of them next to the rows: spills)
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = (int)lane + i * 32;
-    if (idx < nvec) {
-      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float4 o;
-        o.x = (v[r][i].x - mean[r]) * rstd[r] * g.x + b.x;
-        o.y = (v[r][i].y - mean[r]) * rstd[r] * g.y + b.y;
-        o.z = (v[r][i].z - mean[r]) * rstd[r] * g.z + b.z;
-        o.w = (v[r][i].w - mean[r]) * rstd[r] * g.w + b.w;
-        const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
-        uint2 h;
-        h.x = *reinterpret_cast<const uint32_t*>(&h01);
-        h.y = *reinterpret_cast<const uint32_t*>(&h23);
-        __half* orow = o0 + r * o_pitch;
-        reinterpret_cast<uint2*>(orow)[idx] = h;
-        if (split) {
-          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          uint2 l;
-          l.x = pack_half2(o.x - f01.x, o.y - f01.y);
-          l.y = pack_half2(o.z - f23.x, o.w - f23.y);
-          reinterpret_cast<uint2*>(orow + E)[idx] = l;
-        }
-      }
-    }
-  }
-}
-
 // SPLIT ("fp32x3" precision): both operands are stored as fp16 hi | lo halves along K (A [M,2K], B [N,2K]); the K loop
 // runs hi*hi + lo*hi + hi*lo (three passes over the same fp32 accumulator: 22 significand bits per operand, the
 // dropped lo*lo term is 2^-22 relative), and fp16 outputs are written as hi | lo pairs as well (lo part p.lo_col_off
@@ -166,11 +72,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * STAGES;                // [ACC_STAGES] one per CTA
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] used in the leader CTA only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
-  // fused LayerNorm (EPI_BIAS_RESIDUAL, p.ln_counter): slabs this CTA has to normalise, handed from the two epilogue
-  // issuers to the two LayerNorm warps (2 and 3) through one 8-deep queue per warp (entry = slab + 1, 0 = empty)
-  volatile int* ln_q = reinterpret_cast<volatile int*>(tmem_slot + 2);  // [2][8]
-  int* ln_tail = const_cast<int*>(ln_q) + 16;                           // next queue slot (shared-memory atomic)
-  volatile int* ln_done = ln_q + 17;                                    // issuers that have pushed their last slab
 
   const uint32_t warp = threadIdx.x / 32;
   const uint32_t lane = threadIdx.x % 32;
@@ -220,7 +121,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_alloc_pair(tmem_slot, TMEM_COLS);
     tmem_relinquish_pair();
   }
-  if (warp == 3 && lane < 18) ln_q[lane] = 0;  // queues, tail, done
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -277,57 +177,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ===================== fused LayerNorm warps (EPI_BIAS_RESIDUAL with p.ln_counter) =====================
-    // Own warps, own registers: the row lives in registers (two-pass mean / variance like layernorm_rows_kernel, so the
-    // result has the bits of the stand-alone kernel) and nothing may spill — with ~213 KB of the SM carved out as shared
-    // memory the L1 is tiny and a spilled value is an L2 round trip (a version inside the epilogue warps, which ptxas
-    // spilled, took 130 us per row).  Warp 2 normalises rows [0,128) of a queued slab, warp 3 rows [128,256).
-    if constexpr (EPI == EPI_BIAS_RESIDUAL) {
-      if (p.ln_counter != nullptr && !(p.ln_debug & 8)) {
-        volatile int* q = ln_q + (warp - 2) * 8;
-        int head = 0;
-        for (;;) {
-          int v = 0;
-          if (lane == 0) v = q[head & 7];
-          v = __shfl_sync(0xffffffffu, v, 0);
-          if (v == 0) {
-            int d = 0;
-            if (lane == 0) d = *ln_done;
-            d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == 2) {  // both issuers have pushed everything: one last look at the queue
-              if (lane == 0) v = q[head & 7];
-              v = __shfl_sync(0xffffffffu, v, 0);
-              if (v == 0) break;
-            } else {
-              __nanosleep(256);
-              continue;
-            }
-          }
-          const int r0 = (v - 1) * PAIR_M + (int)(warp - 2) * 128;
-          const int pitch = (p.ln_split ? 2 : 1) * p.N;
-          const float* xbase = reinterpret_cast<const float*>(p.out);
-          __half* obase = reinterpret_cast<__half*>(p.ln_out);
-          const int nrows = min(128, p.M - r0);  // may be <= 0 for the second half of a partial last slab
-          int r = 0;
-          if (p.N <= 10 * 128) {
-            for (; r + 2 <= nrows; r += 2)
-              warp_layernorm_rows<10, 2>(xbase + (size_t)(r0 + r) * p.ldo, p.ldo, p.ln_gamma, p.ln_beta,
-                                         obase + (size_t)(r0 + r) * pitch, pitch, p.N, p.ln_eps, p.ln_split, lane);
-            for (; r < nrows; ++r)
-              warp_layernorm_rows<10, 1>(xbase + (size_t)(r0 + r) * p.ldo, p.ldo, p.ln_gamma, p.ln_beta,
-                                         obase + (size_t)(r0 + r) * pitch, pitch, p.N, p.ln_eps, p.ln_split, lane);
-          } else {
-            for (; r < nrows; ++r)
-              warp_layernorm_rows<20, 1>(xbase + (size_t)(r0 + r) * p.ldo, p.ldo, p.ln_gamma, p.ln_beta,
-                                         obase + (size_t)(r0 + r) * pitch, pitch, p.N, p.ln_eps, p.ln_split, lane);
-          }
-          __syncwarp();
-          if (lane == 0) q[head & 7] = 0;
-          ++head;
-        }
-      }
-    }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue: TMEM -> regs -> swizzled smem -> TMA store / reduce =====================
     const uint32_t ew = warp - FIRST_EPI_WARP;
@@ -340,33 +189,11 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int iter = 0;
     [[maybe_unused]] float rc[32], rs[32];  // EPI_QKV_ROPE: cos / sin of this thread's row
     [[maybe_unused]] int rope_blk = -1;
-    // EPI_BIAS_RESIDUAL + fused LayerNorm (p.ln_counter): the slab of the previous tile, whose reduce-adds are retired
-    // one tile later (they have had a whole tile to complete, so the wait does not stall)
-    [[maybe_unused]] int ln_prev_blk = -1;
-    [[maybe_unused]] const bool fuse_ln = (EPI == EPI_BIAS_RESIDUAL) && p.ln_counter != nullptr;
-    [[maybe_unused]] const int ln_target = 4 * tiles_n;  // 2 CTAs x 2 column halves arrive once per column tile
-    // retire the reduce-adds of slab `blk` (at most `pending` younger bulk groups stay in flight), count the arrival and,
-    // as the last arriver, queue the slab for normalisation by this CTA
-    auto ln_arrive = [&](int blk, int pending) {
-      if (!(p.ln_debug & 1)) tma_store_wait_pending(pending);
-      if (p.ln_debug & 4) return;
-      if (!(p.ln_debug & 2)) __threadfence();
-      const int old = atomicAdd(p.ln_counter + blk, 1);
-      if (old == ln_target - 1) {  // last of the 4 * tiles_n arrivals: every column tile of the slab is in L2
-        p.ln_counter[blk] = 0;     // ready for the next launch (stream-ordered after this kernel)
-        if (!(p.ln_debug & 2)) __threadfence();
-        const int slot = atomicAdd(ln_tail, 1) & 7;
-        while (ln_q[slot] != 0 || ln_q[8 + slot] != 0) __nanosleep(64);  // queue full: the LayerNorm warps are 8 slabs behind
-        ln_q[slot] = blk + 1;
-        ln_q[8 + slot] = blk + 1;
-      }
-    };
     for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
       const int row0 = m_blk * PAIR_M + rank * BLOCK_M;
       const int row = row0 + row_local;
-      [[maybe_unused]] int ln_groups = 0;  // bulk groups this issuer commits for this tile (fused LayerNorm)
       if constexpr (EPI == EPI_QKV_ROPE) {  // before the wait: the loads fly while the tile is still being multiplied
       // cos/sin of this thread's token position, 64 registers, reloaded only when the 256-row slab changes (tiles are
       // walked n-fastest, so once per tiles_n tiles) — r01 re-read them from L2 for every 64-column head group
@@ -691,7 +518,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if constexpr (EPI == EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tmap_out, stg, col, row0);
             else tma_store_2d(&tmap_out, stg, col, row0);
             tma_store_commit();
-            ++ln_groups;
           }
           ++store_iter;
         }
@@ -700,21 +526,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);
-      if constexpr (EPI == EPI_BIAS_RESIDUAL) {
-        if (fuse_ln && issuer) {  // after the accumulator stage has been handed back
-          if (ln_prev_blk >= 0) ln_arrive(ln_prev_blk, ln_groups);
-          ln_prev_blk = m_blk;
-        }
-      }
     }
     if (issuer) tma_store_wait_all();
-    if constexpr (EPI == EPI_BIAS_RESIDUAL) {
-      if (fuse_ln && issuer) {  // the last tile of this cluster: everything is complete now
-        if (ln_prev_blk >= 0) ln_arrive(ln_prev_blk, 0);
-        __threadfence_block();
-        atomicAdd(const_cast<int*>(ln_done), 1);
-      }
-    }
   }
 
   tc_fence_before();

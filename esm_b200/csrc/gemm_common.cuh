@@ -33,16 +33,6 @@ struct GemmParams {
   float q_scale;          // head_dim^-0.5
   int chunked;            // tile walk: 1 = one contiguous run of tiles per cluster (see gemm2.cuh)
   int lo_col_off;         // SPLIT kernels with fp16 output: the lo half of column c is written at column c + lo_col_off
-  // EPI_BIAS_RESIDUAL with a fused LayerNorm of the updated rows (the LayerNorm that FOLLOWS this GEMM, modules.py:137 /
-  // :124 of the next layer): the CTA whose reduce-add completes the last column tile of a 256-row slab re-reads those
-  // rows (hot in L2) and writes the normalised fp16 A operand of the next GEMM.  NULL ln_counter = no fusion.
-  const float* ln_gamma;
-  const float* ln_beta;
-  float ln_eps;
-  void* ln_out;           // fp16 [M, N], or [M, 2N] hi | lo when ln_split
-  int ln_split;
-  int* ln_counter;        // [ceil(M/256)] arrival counters, zero before the first launch; the last arriver resets its slab
-  int ln_debug;           // developer bits (ESMB200_LN_DEBUG): 1 skip the bulk wait, 2 skip fences, 4 skip arrivals, 8 skip service
 };
 
 

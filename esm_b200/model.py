@@ -435,7 +435,7 @@ class ContactPredictionHead(nn.Module):
             "keep": tokens.ne(self.eos_idx).to(torch.uint8).contiguous() if self.append_eos else None,
             "acc": torch.zeros((B, S, S), dtype=torch.float32, device=dev),
             "row": torch.empty((num_layers, B, num_heads, 4 * nt, S), dtype=torch.float32, device=dev),
-            "col": torch.empty((num_layers, B, num_heads, nt, S), dtype=torch.float32, device=dev),
+            "col": torch.empty((num_layers, B, num_heads, 4 * nt, S), dtype=torch.float32, device=dev),
             "w": _f32(self.regression.weight).view(num_layers, num_heads).contiguous(),
         }
         job = _lib.ContactJob()

@@ -104,7 +104,7 @@ typedef struct esmb200_contact_job {
   const uint8_t* keep;  /* [B,T] 1 = not <eos>, or NULL */
   float* acc;           /* [B,S,S]  += sum_{l,h} w[l,h] A_{l,h}; zeroed by the caller */
   float* row_part;      /* [n_layers,B,H,4*nt,S] row sums of A_{l,h} per 32-key quarter tile (sum over 4*nt = rowsum) */
-  float* col_part;      /* [n_layers,B,H,nt,S] column sums per 128-query tile (sum over nt = colsum) */
+  float* col_part;      /* [n_layers,B,H,4*nt,S] column sums per 32-query quarter tile (sum over 4*nt = colsum) */
   int32_t lo, hi;       /* cropped positions [lo,hi): 1 .. T-1 for <cls> ... <eos> */
 } esmb200_contact_job;
 
@@ -254,7 +254,6 @@ int esmb200_attention_split(const void* qkv, const uint8_t* pad_mask, void* ctx,
  * "attn"      8 (default: attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, 2 CTAs/SM)          env ESMB200_ATTN
  * "attn_poly" 0 | 2 | 3 | 4 (default): every n-th pair of softmax exponentials on the FMA pipe   env ESMB200_ATTN_POLY
  * "pdl"       0 (default) | 1: programmatic dependent launch between the layer's kernels        env ESMB200_PDL
- * "fuse_ln"   1 (default) | 0: LayerNorm in the tail of the residual GEMMs instead of separate kernels    env ESMB200_FUSE_LN
  * Returns ESMB200_EINVAL for an unknown name or value. Not thread-safe against concurrent launches. */
 int esmb200_set_option(const char* name, int32_t value);
 
