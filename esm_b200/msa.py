@@ -308,9 +308,10 @@ class MSATransformer(nn.Module):
     `model(tokens [B,R,C], repr_layers, need_head_weights, return_contacts)` -> dict with `logits`,
     `representations`, and — when asked — `row_attentions`, `col_attentions`, `contacts`.
 
-    Deviation: `return_contacts=True` alone returns `row_attentions` and `contacts` but not `col_attentions` (the
-    reference materialises the [B,L,H,C,R,R] column maps as a side effect, 4.8 GB for a 128 x 512 MSA); pass
-    `need_head_weights=True` to get them."""
+    `return_contacts=True` implies `need_head_weights=True` like the reference (msa_transformer.py:149-150), i.e. the
+    result also carries `col_attentions` [B,L,H,C,R,R] (4.8 GB for a 128 x 512 MSA).  `predict_contacts()` — which only
+    returns the contacts — skips the column maps; set `model.contacts_without_col_attentions = True` to get the same
+    saving from `model(tokens, return_contacts=True)`."""
 
     def __init__(self, args: Union[Namespace, dict, None] = None, alphabet: Union[Alphabet, str] = "MSA Transformer",
                  **kwargs):
@@ -351,6 +352,8 @@ class MSATransformer(nn.Module):
         self.emb_layer_norm_after = nn.LayerNorm(E)
         self.lm_head = RobertaLMHead(embed_dim=E, output_dim=self.alphabet_size, weight=self.embed_tokens.weight)
 
+    contacts_without_col_attentions = False  # True: return_contacts alone does not materialise col_attentions
+
     @property
     def num_layers(self) -> int:
         return self.args.layers
@@ -364,6 +367,8 @@ class MSATransformer(nn.Module):
         assert tokens.ndim == 3
         if not tokens.is_cuda:
             raise _lib.Esmb200Error("esm_b200 runs on CUDA (sm_100a) only: pass tokens.cuda(); no CPU fallback")
+        if return_contacts and not self.contacts_without_col_attentions:
+            need_head_weights = True  # msa_transformer.py:149-150
         lib = _lib.load()
         tokens = tokens.contiguous()
         B, R, C = tokens.shape
@@ -429,4 +434,10 @@ class MSATransformer(nn.Module):
         return result
 
     def predict_contacts(self, tokens):
-        return self(tokens, return_contacts=True)["contacts"]
+        """msa_transformer.py:222-223; only the contacts are returned, so the column attention maps are not built."""
+        prev = self.contacts_without_col_attentions
+        self.contacts_without_col_attentions = True
+        try:
+            return self(tokens, return_contacts=True)["contacts"]
+        finally:
+            self.contacts_without_col_attentions = prev

@@ -107,7 +107,11 @@ def test_msa_transformer_against_reference_golden(name, golden_dir):
     keep = tokens.ne(1)
     L = cfg["layers"]
     out = model(tokens.cuda(), repr_layers=[0, 1, L], return_contacts=True)
-    assert "col_attentions" not in out
+    assert "col_attentions" in out  # return_contacts implies need_head_weights (msa_transformer.py:149-150)
+    model.contacts_without_col_attentions = True
+    lean = model(tokens.cuda(), repr_layers=[L], return_contacts=True)
+    model.contacts_without_col_attentions = False
+    assert "col_attentions" not in lean and float((lean["contacts"] - out["contacts"]).abs().max()) <= 1e-4
     for k, v in fx["representations"].items():
         assert rel_fro(out["representations"][k].cpu()[keep], v[keep]) <= (1e-5 if k == 0 else 3e-3), k
     assert rel_fro(out["logits"].cpu()[keep], fx["logits"][keep]) <= 4e-3

@@ -106,6 +106,7 @@ def test_msa1b_full_depth_32x256_padded_vs_oracle():
     model.load_state_dict(sd, strict=True)
     model = model.eval().cuda()
     tokens = msa_oracle.make_msa_tokens(2, 32, 256, seed=8, pad_cols=19, pad_rows_last=5)
+    model.contacts_without_col_attentions = True  # the [B,L,H,C,R,R] column maps are covered by tests/test_gpu_msa.py
     out = model(tokens.cuda(), repr_layers=[6, 12], return_contacts=True)
     torch.cuda.synchronize()
     ref = msa_oracle.msa_transformer_forward(sd, L, H, tokens, repr_layers=[6, 12], return_contacts=True)
