@@ -150,22 +150,10 @@ int attn_poly() {
   return g_attn_poly;
 }
 
-int g_attn_ctas = -1;
-int attn_ctas() {
-  if (g_attn_ctas < 0) {
-    const char* e = getenv("ESMB200_ATTN_CTAS");
-    g_attn_ctas = (e && e[0] == '3') ? 3 : 4;
-  }
-  return g_attn_ctas;
-}
-
 cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& ap, int sms,
                                  cudaStream_t st) {
   if (ap.lo_off > 0) return launch_attention_v8_poly<0, true>(tq, tkv, ap, sms, st);  // fp32x3: all exponentials on MUFU
   if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
-  if (attn_ctas() == 3)
-    return attn_poly() == 0 ? launch_attention_v8_poly<0, false, 3>(tq, tkv, ap, sms, st)
-                            : launch_attention_v8_poly<4, false, 3>(tq, tkv, ap, sms, st);
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
     case 2: return launch_attention_v8_poly<2>(tq, tkv, ap, sms, st);
@@ -1118,7 +1106,6 @@ int esmb200_set_option(const char* name, int32_t value) {
     return ESMB200_OK;
   }
   if (!strcmp(name, "pdl") && (value == 0 || value == 1)) { pdl_flag() = value; return ESMB200_OK; }
-  if (!strcmp(name, "attn_ctas") && (value == 3 || value == 4)) { g_attn_ctas = value; return ESMB200_OK; }
   return fail(ESMB200_EINVAL, std::string("unknown option or value: ") + name);
 }
 

@@ -23,6 +23,8 @@
 // 11-bit significand), row sums and O are fp32.
 //
 // TMEM (128 columns per CTA, 4 CTAs/SM = all 512): S/P [0,64) | O [64,128).
+// (A 3-CTA/SM build — 96 registers, both 32-column S loads of a block in flight behind one wait — measured slower:
+// 2.32-2.47 ms vs 2.04-2.06 ms at B = 256, profiles/r02_attention_sweep.txt: occupancy beats per-warp load depth.)
 #pragma once
 
 #include "attention_common.cuh"
@@ -82,9 +84,8 @@ __device__ __forceinline__ void attn8_exp_half(const uint32_t (&sv)[32], uint32_
   }
 }
 
-// CTAS: resident CTAs per SM the kernel is compiled for (4 = 80 registers per thread, 3 = 112: A/B knob "attn_ctas")
-template <int POLY, bool SPLIT = false, int CTAS = attn8_cfg::CTAS_PER_SM>
-__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, SPLIT ? attn8_cfg::CTAS_PER_SM_SPLIT : CTAS)
+template <int POLY, bool SPLIT = false>
+__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, SPLIT ? attn8_cfg::CTAS_PER_SM_SPLIT : attn8_cfg::CTAS_PER_SM)
 attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                         const AttnParams p) {
   using namespace attn8_cfg;
@@ -279,23 +280,11 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int trip = 0;; ++trip) {
           const float mneg = -m_ref * LOG2E;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
-          [[maybe_unused]] uint32_t sv2[2][32];
-          if constexpr (CTAS == 3 && !SPLIT) {  // 112 registers per thread: both halves of the block in flight, ONE wait
-            tmem_ld_32x32b_x32(ts, sv2[0]);
-            tmem_ld_32x32b_x32(ts + 32, sv2[1]);
-            tmem_wait_ld_dep(sv2[0]);
-            reg_fence(sv2[1]);
-          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t sv[32];
-            if constexpr (CTAS == 3 && !SPLIT) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) sv[i] = sv2[c][i];
-            } else {
-              tmem_ld_32x32b_x32(ts + c * 32, sv);
-              tmem_wait_ld_dep(sv);
-            }
+            tmem_ld_32x32b_x32(ts + c * 32, sv);
+            tmem_wait_ld_dep(sv);
             if constexpr (SPLIT) {
               const uint32_t wd = kw[c];
 #pragma unroll
@@ -419,19 +408,18 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-template <int POLY, bool SPLIT = false, int CTAS = attn8_cfg::CTAS_PER_SM>
+template <int POLY, bool SPLIT = false>
 inline cudaError_t launch_attention_v8_poly(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const AttnParams& p,
                                             int num_sms, cudaStream_t stream) {
   using namespace attn8_cfg;
   constexpr int smem = SPLIT ? SMEM_BYTES_SPLIT : SMEM_BYTES;
-  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY, SPLIT, CTAS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem);
   if (e != cudaSuccess) return e;
   const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
-  const long long cap = (long long)(SPLIT ? CTAS_PER_SM_SPLIT : CTAS) * num_sms;
+  const long long cap = (long long)(SPLIT ? CTAS_PER_SM_SPLIT : CTAS_PER_SM) * num_sms;
   const int grid = (int)(total < cap ? total : cap);
-  return launch_pdl(attention_fwd_kernel_v8<POLY, SPLIT, CTAS>, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q,
-                    tmap_kv, p);
+  return launch_pdl(attention_fwd_kernel_v8<POLY, SPLIT>, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, p);
 }
 
 }  // namespace esmb200

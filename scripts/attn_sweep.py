@@ -52,7 +52,7 @@ def main():
     H = 20
     E = 64 * H
     out = {"correctness": {}, "timing": {}}
-    variants = [("v7", 7, 3, 4)] + [(f"v8_poly{p}", 8, p, 4) for p in (0, 2, 3, 4)] + [("v8_poly0_3cta", 8, 0, 3), ("v8_poly4_3cta", 8, 4, 3)]
+    variants = [("v7", 7, 3, 4)] + [(f"v8_poly{p}", 8, p, 4) for p in (0, 2, 3, 4)]
     # ---- correctness: ragged batch, sharp logits (gain), partial last blocks
     g = torch.Generator().manual_seed(3)
     for gain in (1.0, 4.0):
@@ -68,7 +68,6 @@ def main():
         for name, ver, poly, ctas in variants:
             L.check(lib.esmb200_set_option(b"attn", ver))
             L.check(lib.esmb200_set_option(b"attn_poly", poly))
-            L.check(lib.esmb200_set_option(b"attn_ctas", ctas))
             ctx = torch.zeros(B * T, E, dtype=torch.float16, device=dev)
             L.check(lib.esmb200_attention(P(qkv), P(mask), P(ctx), None, B, T, H, P(scratch), S()))
             torch.cuda.synchronize()
@@ -87,7 +86,6 @@ def main():
         for name, ver, poly, ctas in variants:
             L.check(lib.esmb200_set_option(b"attn", ver))
             L.check(lib.esmb200_set_option(b"attn_poly", poly))
-            L.check(lib.esmb200_set_option(b"attn_ctas", ctas))
             ms = timeit(lambda: L.check(lib.esmb200_attention(P(qkv), None, P(ctx), None, B, T, H, P(scratch), S())))
             tf = 4.0 * B * H * T * T * 64 / ms / 1e9
             out["timing"][f"{name}_B{B}"] = {"ms": ms, "TFLOP/s": tf}
