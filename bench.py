@@ -324,8 +324,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # no NCCL version banner on stdout: stdout carries ONE JSON line
+        # stdout carries ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION and above (WARN
+        # included), so nothing is set here; a caller who exports NCCL_DEBUG=INFO gets NCCL's lines, then the JSON line last
         dist.init_process_group("nccl", device_id=dev)
 
     from esm_b200 import _lib, pretrained

@@ -186,6 +186,37 @@ def test_attention_reference_max_raise(dev):
     torch.testing.assert_close(probs, ref_p, atol=1e-4, rtol=1e-3)
 
 
+def test_attention_left_and_interior_padding_with_very_negative_scores(dev):
+    """when the first key block is fully padded the reference maximum must be seeded from the first block that
+    has an attendable key — with scores around -40 a reference of 0 would round every probability to 0 in fp16.  Left
+    padding (first 130 keys) and an interior gap, all valid logits ~ -40."""
+    L = _lib(); lib = L.load()
+    B, T, H = 2, 400, 2
+    E = 64 * H
+    g = torch.Generator(device="cpu").manual_seed(17)
+    u = torch.randn(64, generator=g)
+    u = u / u.norm() * (40.0 ** 0.5)
+    qkv = 0.05 * torch.randn(B * T, 3 * E, generator=g)
+    for h in range(H):
+        qkv[:, h * 64:(h + 1) * 64] += u
+        qkv[:, E + h * 64:E + (h + 1) * 64] -= u
+    qkv[:, 2 * E:] = torch.randn(B * T, E, generator=g)
+    qkv = qkv.half().to(dev)
+    pad = torch.zeros(B, T, dtype=torch.uint8)
+    pad[0, :130] = 1            # left padding: blocks 0 and 1 (64-key blocks) fully masked, block 2 partially
+    pad[1, 64:200] = 1          # interior gap
+    pad[1, 390:] = 1
+    pad = pad.to(dev)
+    ctx = torch.full((B * T, E), float("nan"), dtype=torch.float16, device=dev)
+    probs = torch.full((B, H, T, T), float("nan"), device=dev)
+    scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
+    L.check(lib.esmb200_attention(P(qkv), P(pad), P(ctx), P(probs), B, T, H, P(scratch), S()))
+    ref_o, ref_p = _attention_ref(qkv, pad, B, T, H)
+    assert float(ref_o.abs().max()) > 0.05
+    torch.testing.assert_close(ctx.float(), ref_o, atol=4e-3, rtol=4e-3)
+    torch.testing.assert_close(probs, ref_p, atol=2e-5, rtol=1e-3)
+
+
 def test_embed_tokens(dev):
     from oracle import esm2_oracle
     from oracle.weights import make_state_dict, make_tokens
