@@ -41,6 +41,8 @@ def create_parser():
     p.add_argument("--repr_layers", type=int, default=[-1], nargs="+")
     p.add_argument("--include", type=str, nargs="+", choices=list(INCLUDE_CHOICES), required=True)
     p.add_argument("--truncation_seq_length", type=int, default=1022)
+    p.add_argument("--precision", choices=["fp16", "fp32x3"], default="fp16",
+                   help="fp16: fp16 MMA operands (default, fastest); fp32x3: hi+lo operand pairs, fp32-grade results (~2.6x slower)")
     return p
 
 
@@ -155,6 +157,8 @@ def run(args) -> int:
     if getattr(model, "random_init", False):
         raise RuntimeError("refusing to write embeddings of a random-init model: give --model_location a checkpoint")
     model = model.eval().to(dev)
+    if getattr(args, "precision", "fp16") != "fp16":
+        model.set_precision(args.precision)
     n_layers = model.num_layers
     if not all(-(n_layers + 1) <= i <= n_layers for i in args.repr_layers):
         raise ValueError(f"--repr_layers must lie in [-{n_layers + 1}, {n_layers}]")
