@@ -41,6 +41,31 @@ def main():
         res[f"B{B}"] = {"pdl_on_ms": sorted(times[1]), "pdl_off_ms": sorted(times[0])}
         print(f"B={B}: PDL on {min(times[1]):.3f} ms (median {sorted(times[1])[2]:.3f}), off {min(times[0]):.3f} ms "
               f"(median {sorted(times[0])[2]:.3f})")
+    del model
+    # configs[4]: the MSA axial stack is ~180 SHORT, non-persistent launches per forward -- the one place a tail exists
+    msa, _ = pretrained.load_msa_model_and_alphabet("esm_msa1b_t12_100M_UR50S", allow_random_init=True, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    mtok = torch.randint(4, 24, (1, 128, 512), generator=g)
+    mtok[:, :, 0] = 0
+    mtok = mtok.cuda()
+    times = {0: [], 1: []}
+    for rep in range(4):
+        for pdl in (1, 0):
+            _lib.check(lib.esmb200_set_option(b"pdl", pdl))
+            for _ in range(2):
+                msa(mtok, repr_layers=[12])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                msa(mtok, repr_layers=[12])
+            b.record()
+            torch.cuda.synchronize()
+            times[pdl].append(a.elapsed_time(b) / 5)
+    res["msa_128x512"] = {"pdl_on_ms": sorted(times[1]), "pdl_off_ms": sorted(times[0])}
+    print(f"MSA 128x512: PDL on {min(times[1]):.3f} ms (median {sorted(times[1])[2]:.3f}), off {min(times[0]):.3f} ms "
+          f"(median {sorted(times[0])[2]:.3f})")
+    _lib.check(lib.esmb200_set_option(b"pdl", 0))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "pdl_ab.json"), "w"), indent=1)
 
