@@ -17,7 +17,9 @@ try:
 except Exception as e: print(' parse failed',e)
 PY
 }
-run 1; run 8; run 4; run 2
+run 1; run 8
+if [ "$1" != full ]; then exit 0; fi
+run 4; run 2
 echo "== reference arm under torchrun N=2 (rank 0 only works)"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -2 | cut -c1-400
 echo "== PDL A/B incl. MSA"; timeout 600 python scripts/pdl_ab.py 2>/dev/null | tail -4
