@@ -30,6 +30,7 @@ EXPORTS = (
     "esmb200_gemm_qkv_f16",
     "esmb200_attention_scratch_bytes",
     "esmb200_attention",
+    "esmb200_attention128",
     "esmb200_tied_row_attention_scratch_bytes",
     "esmb200_tied_row_attention",
     "esmb200_column_attention",
@@ -171,6 +172,9 @@ def _declare(lib):
     lib.esmb200_gemm_split.restype = c_int32
     lib.esmb200_gemm_split.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                        c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.esmb200_attention128.restype = c_int32
+    lib.esmb200_attention128.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                         c_void_p]
     lib.esmb200_attention_split.restype = c_int32
     lib.esmb200_attention_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                             c_void_p]

@@ -153,6 +153,7 @@ int attn_poly() {
 cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& ap, int sms,
                                  cudaStream_t st) {
   if (ap.lo_off > 0) return launch_attention_v8_poly<0, true>(tq, tkv, ap, sms, st);  // fp32x3: all exponentials on MUFU
+  if (ap.slots == 2) return launch_attention_v8_poly<4, false, 2>(tq, tkv, ap, sms, st);  // head_dim <= 128 (15B)
   if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
@@ -161,6 +162,9 @@ cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, 
     default: return launch_attention_v8_poly<4>(tq, tkv, ap, sms, st);
   }
 }
+
+// 64-wide column slots per head on the attention side: 1 for head_dim <= 64, 2 up to 128 (elementwise.cuh head_slot)
+inline int head_slots(int E, int H) { return (H > 0 && E / H > 64) ? 2 : 1; }
 
 int qkv_chunked() {  // tile walk of the QKV GEMM (gemm2.cuh): 1 = one contiguous run of tiles per cluster (default)
   static const int v = [] {
@@ -285,8 +289,9 @@ struct ContactLayer {
 
 int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batch_stride, int attn_flags,
                   const AttnScratch& s, int B, int T, int H, cudaStream_t st, bool split = false,
-                  const ContactLayer* contact = nullptr) {
-  const int E = H * 64;
+                  const ContactLayer* contact = nullptr, int slots = 1) {
+  const int E = H * 64 * slots;
+  if (slots == 2 && split) return fail(ESMB200_EINVAL, "head_dim > 64: fp32x3 precision is not available");
   const uint64_t qcols = (uint64_t)(split ? 6 : 3) * E;  // fp32x3: [q k v]_hi | [q k v]_lo
   CUtensorMap tq;
   int rc = make_tmap_f16(&tq, qkv, (uint64_t)B * T, qcols, qcols, 128);
@@ -294,6 +299,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
   AttnParams ap;
   ap.B = B; ap.T = T; ap.H = H; ap.E = E;
   ap.lo_off = split ? 3 * E : 0;
+  ap.slots = slots;
   ap.keybits = s.keybits; ap.kvlen = s.kvlen; ap.words = s.words;
   ap.ctx = static_cast<__half*>(ctx);
   ap.row_max = probs ? s.row_max : nullptr;
@@ -311,7 +317,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
     // probabilities written once and folded into the contact accumulators in the same pass (attention_contact.cuh)
     if (B > 65535) return fail(ESMB200_EINVAL, "return_contacts: B must be <= 65535");
     ContactFuseParams cp;
-    cp.B = B; cp.T = T; cp.H = H; cp.E = E;
+    cp.B = B; cp.T = T; cp.H = H; cp.E = E; cp.slots = slots;
     cp.keybits = s.keybits; cp.kvlen = s.kvlen; cp.words = s.words;
     cp.row_max = s.row_max; cp.row_sum = s.row_sum; cp.probs = probs;
     cp.batch_stride = probs_batch_stride > 0 ? probs_batch_stride : (long long)H * T * T;
@@ -334,6 +340,7 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
     pp.batch_stride = probs_batch_stride > 0 ? probs_batch_stride : (long long)H * T * T;
     pp.zero_pad_rows = attn_flags & 1;
     pp.lo_off = split ? 3 * E : 0;
+    pp.slots = slots;
     {
       ProfScope ps(T_PROBS, st);
       e = launch_attention_probs(tq, pp, st);
@@ -350,16 +357,17 @@ int run_attention(const void* qkv, void* ctx, float* probs, long long probs_batc
 // ---------------------------------------------------------------------------------------------------------------
 struct esmb200_layer {
   int E, H, F;
-  int d;          // head_dim (<= 64); every head occupies a 64-wide slot of the attention-side tensors
-  int Ea;         // 64 * H: width of q / k / v / ctx
+  int d;          // head_dim (<= 128); every head occupies `slots` 64-wide slots of the attention-side tensors
+  int slots;      // 1 (d <= 64) or 2 (64 < d <= 128, ESM-2 15B)
+  int Ea;         // 64 * slots * H: width of q / k / v / ctx
   float q_scale;  // d^-1/2 (multihead_attention.py:100)
   int split;      // 1: fp32x3 precision — weights packed as fp16 hi | lo along K, activations likewise
   float eps;
   // borrowed fp32 parameters (owned by the caller, must outlive the layer)
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *out_b, *fc1_b, *fc2_b;
   // owned packed copies
-  __half* w_qkv;  // [3*Ea, E]: row s*Ea + h*64 + slot(j) <- W_s row h*d + j, zero rows elsewhere
-  __half* w_out;  // [E, Ea]: column h*64 + slot(j) <- out_proj.weight column h*d + j
+  __half* w_qkv;  // [3*Ea, E]: row s*Ea + head_slot(h*d + j) <- W_s row h*d + j, zero rows elsewhere
+  __half* w_out;  // [E, Ea]: column head_slot(h*d + j) <- out_proj.weight column h*d + j
   __half* w_fc1;  // [F,E]
   __half* w_fc2;  // [E,F]
   float* b_qkv;   // [3*Ea]
@@ -401,16 +409,17 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
   const int E = w->embed_dim, H = w->num_heads, F = w->ffn_dim;
   if (E <= 0 || H <= 0 || E % H != 0) return fail(ESMB200_EINVAL, "embed_dim must be a positive multiple of num_heads");
   const int d = w->head_dim > 0 ? w->head_dim : E / H;
-  if (d * H != E || d > 64 || d % 2 != 0)
-    return fail(ESMB200_EINVAL, "esmb200 supports even head_dim <= 64 (ESM-2 8M..3B, MSA Transformer); 15B (128) is not");
+  if (d * H != E || d > 128 || d % 2 != 0)
+    return fail(ESMB200_EINVAL, "esmb200 supports even head_dim <= 128 (every ESM-2 model, MSA Transformer)");
   if (E % 16 != 0) return fail(ESMB200_EINVAL, "embed_dim must be a multiple of 16");
   const bool has_ffn = w->fc1_weight != nullptr;  // NULL fc1_weight: attention-only layer (MSA row-attention sub-layer)
   if (has_ffn && (F <= 0 || F % 64 != 0)) return fail(ESMB200_EINVAL, "ffn_dim must be a positive multiple of 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   esmb200_layer* L = new esmb200_layer();
   memset(static_cast<void*>(L), 0, sizeof(*L));
-  const int Ea = 64 * H;
-  L->E = E; L->H = H; L->F = has_ffn ? F : 0; L->d = d; L->Ea = Ea; L->eps = w->ln_eps;
+  const int slots = head_slots(E, H);
+  const int Ea = 64 * slots * H;
+  L->E = E; L->H = H; L->F = has_ffn ? F : 0; L->d = d; L->slots = slots; L->Ea = Ea; L->eps = w->ln_eps;
   L->q_scale = 1.0f / sqrtf((float)d);
   L->ln1_w = w->ln1_weight; L->ln1_b = w->ln1_bias; L->ln2_w = w->ln2_weight; L->ln2_b = w->ln2_bias;
   L->out_b = w->out_bias; L->fc1_b = w->fc1_bias; L->fc2_b = w->fc2_bias;
@@ -419,6 +428,10 @@ int esmb200_layer_create(const esmb200_layer_weights* w, void* stream, esmb200_l
     return fail(ESMB200_EINVAL, "precision must be 0 (fp16 operands) or 1 (fp32x3: fp16 hi|lo operands)");
   }
   const int split = w->precision;
+  if (split && slots == 2) {
+    delete L;
+    return fail(ESMB200_EINVAL, "fp32x3 precision is not available for head_dim > 64");
+  }
   if (split && (E % 64 != 0 || (has_ffn && F % 64 != 0))) {
     delete L;
     return fail(ESMB200_EINVAL, "fp32x3 precision needs embed_dim % 64 == 0 (all ESM-2 models except 35M)");
@@ -502,7 +515,7 @@ size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T) {
 }
 
 size_t esmb200_workspace_bytes(int32_t E, int32_t H, int32_t F, int32_t B, int32_t T, int32_t precision) {
-  const size_t M = (size_t)B * T, Ea = (size_t)64 * H, pf = precision ? 2 : 1;
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * head_slots(E, H) * H, pf = precision ? 2 : 1;
   const size_t a = align_up(M * E * 2 * pf, 1024);                  // xn fp16 [M,E] (hi | lo)
   const size_t big_qkv_ctx = align_up(M * 3 * Ea * 2 * pf, 1024) + align_up(M * Ea * 2 * pf, 1024);
   const size_t big_h = align_up(M * F * 2 * pf, 1024);
@@ -521,7 +534,7 @@ struct Workspace {
 
 int carve_workspace(Workspace* ws, void* workspace, size_t bytes, int E, int H, int F, int B, int T, int split) {
   if (bytes < esmb200_workspace_bytes(E, H, F, B, T, split)) return fail(ESMB200_EWORKSPACE, "workspace too small");
-  const size_t M = (size_t)B * T, Ea = (size_t)64 * H, pf = split ? 2 : 1;
+  const size_t M = (size_t)B * T, Ea = (size_t)64 * head_slots(E, H) * H, pf = split ? 2 : 1;
   uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
   ws->xn = reinterpret_cast<__half*>(p);
   p += align_up(M * E * 2 * pf, 1024);
@@ -560,10 +573,12 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
   g.M = M; g.N = 3 * Ea; g.K = E; g.bias = L->b_qkv; g.out = ws.qkv; g.ldo = 3 * Ea;
   g.rope_cos = rope_cos; g.rope_sin = rope_sin; g.T = T; g.E = Ea; g.q_scale = L->q_scale; g.chunked = qkv_chunked();
   g.lo_col_off = 3 * Ea;
+  g.rope_ld = 32 * L->slots;
   int rc = launch_gemm(EPI_QKV_ROPE, am.xn, L->tm_qkv, am.qkv_out, g, st, T_QKV, split);
   if (rc) return rc;
   // attention (multihead_attention.py:357-394)
-  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st, split, contact);
+  rc = run_attention(ws.qkv, ws.ctx, attn_probs, attn_batch_stride, attn_flags, ws.as, B, T, H, st, split, contact,
+                     L->slots);
   if (rc) return rc;
   // out_proj + residual (multihead_attention.py:395, modules.py:134)
   memset(&g, 0, sizeof g);
@@ -590,7 +605,7 @@ int layer_forward_impl(esmb200_layer* L, float* x, int B, int T, const float* ro
 }
 
 int make_act_maps(ActMaps* am, const Workspace& ws, const float* x, int E, int H, int F, int M, int split = 0) {
-  const uint64_t Ea = (uint64_t)64 * H, pf = split ? 2 : 1;  // fp32x3: every fp16 activation is [rows, 2 * width]
+  const uint64_t Ea = (uint64_t)64 * head_slots(E, H) * H, pf = split ? 2 : 1;  // fp32x3: activations are [rows, 2 * width]
   int rc = make_tmap_f16(&am->xn, ws.xn, M, pf * E, pf * E, gemm2_cfg::BOX_M);
   if (!rc) rc = make_tmap_f16(&am->ctx, ws.ctx, M, pf * Ea, pf * Ea, gemm2_cfg::BOX_M);
   if (!rc) rc = make_tmap_f16(&am->h, ws.h, M, pf * F, pf * F, gemm2_cfg::BOX_M);
@@ -666,10 +681,13 @@ int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mas
 int esmb200_embed_tokens(const int64_t* tokens, const float* table, float* x, int32_t B, int32_t T, int32_t E,
                          int32_t padding_idx, int32_t mask_idx, int32_t token_dropout, void* stream) {
   if (!tokens || !table || !x) return fail(ESMB200_EINVAL, "null argument");
-  if (B <= 0 || T <= 0 || E % 4 != 0) return fail(ESMB200_EINVAL, "bad shape");
+  if (B <= 0 || B > 65535 || T <= 0 || E % 4 != 0) return fail(ESMB200_EINVAL, "bad shape");
   ProfScope ps(T_EMBED, static_cast<cudaStream_t>(stream));
-  embed_tokens_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, table, x, T, E, padding_idx, mask_idx,
-                                                                        token_dropout);
+  int chunks = (8 * num_sms() + B - 1) / B;  // >= 8 blocks per SM over the batch, at least 4 rows per block
+  if (chunks > (T + 3) / 4) chunks = (T + 3) / 4;
+  if (chunks < 1) chunks = 1;
+  embed_tokens_kernel<<<dim3(chunks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens, table, x, T, E, padding_idx,
+                                                                                     mask_idx, token_dropout);
   CK(cudaGetLastError());
   return ESMB200_OK;
 }
@@ -810,6 +828,18 @@ int esmb200_attention(const void* qkv, const uint8_t* pad_mask, void* ctx, float
   return run_attention(qkv, ctx, attn_probs, 0, 0, s, B, T, H, st);
 }
 
+int esmb200_attention128(const void* qkv, const uint8_t* pad_mask, void* ctx, float* attn_probs, int32_t B, int32_t T,
+                         int32_t H, void* scratch, void* stream) {
+  if (!qkv || !ctx || !scratch) return fail(ESMB200_EINVAL, "null argument");
+  if (B <= 0 || T <= 0 || H <= 0 || H > 64) return fail(ESMB200_EINVAL, "bad shape");
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnScratch s = carve_attn_scratch(scratch, B, T, H);
+  rc = run_key_bits(pad_mask, s, B, T, st);
+  if (rc) return rc;
+  return run_attention(qkv, ctx, attn_probs, 0, 0, s, B, T, H, st, false, nullptr, 2);
+}
 
 // ---- MSA axial attention (esm/axial_attention.py) -----------------------------------------------------------------
 size_t esmb200_tied_row_attention_scratch_bytes(int32_t B, int32_t C, int32_t H) {
@@ -1085,7 +1115,8 @@ int esmb200_mean_pool(const float* x, const int32_t* lengths, float* out, int32_
   if (B <= 0 || T < 2 || E <= 0 || B > 65535) return fail(ESMB200_EINVAL, "bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(T_MEANPOOL, st);
-  dim3 grid((E + 255) / 256, B);
+  if (E % 4 != 0) return fail(ESMB200_EINVAL, "mean_pool needs E % 4 == 0");
+  dim3 grid((E + 127) / 128, B);
   mean_pool_kernel<<<grid, 256, 0, st>>>(x, lengths, out, T, E);
   CK(cudaGetLastError());
   return ESMB200_OK;

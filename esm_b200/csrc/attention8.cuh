@@ -23,6 +23,14 @@
 // 11-bit significand), row sums and O are fp32.
 //
 // TMEM (128 columns per CTA, 4 CTAs/SM = all 512): S/P [0,64) | O [64,128).
+//
+// DS = 2 (64 < head_dim <= 128, ESM-2 15B): a head is TWO 64-wide slots (elementwise.cuh head_slot).  QK^T accumulates
+// both slots into the same S (8 MMAs), P.V runs once per slot into two 64-column halves of O: 256 TMEM columns, twice
+// the shared memory -> 2 CTAs per SM.  Two CTAs do not hide the serial per-CTA chain (first version: 400 TF/s), and
+// 256 columns leave room for a second S buffer: S0 [0,64) | S1 [64,128) | O [128,256).  QK^T(j+1) is issued BEFORE the
+// wait for P_j, so the tensor core fills S_{j+1} while the softmax warps work on S_j.  The "S_{j+1} ready => P.V(j)
+// accumulated" property of the single-buffer pipeline is gone, so the rare reference-max raise waits on pv_done (one
+// commit per P.V) before it rescales O.
 // (A 3-CTA/SM build — 96 registers, both 32-column S loads of a block in flight behind one wait — measured slower:
 // 2.32-2.47 ms vs 2.04-2.06 ms at B = 256, profiles/r02_attention_sweep.txt: occupancy beats per-warp load depth.)
 #pragma once
@@ -46,6 +54,7 @@ constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 1024 + 128;
 // same fp32 accumulator.  Twice the shared memory per tile -> 2 CTAs per SM.
 constexpr int SMEM_BYTES_SPLIT = 2 * Q_BYTES + KV_STAGES * 4 * KV_BYTES + 1024 + 128;
 constexpr int CTAS_PER_SM_SPLIT = 2;
+constexpr int TMEM_COLS_WIDE = 256;    // DS = 2: S/P [0,64) | O [64,192)
 constexpr float SUM_LIMIT = 4096.0f;   // raise the reference when a block's row sum exceeds this
 }  // namespace attn8_cfg
 
@@ -84,13 +93,18 @@ __device__ __forceinline__ void attn8_exp_half(const uint32_t (&sv)[32], uint32_
   }
 }
 
-template <int POLY, bool SPLIT = false>
-__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS, SPLIT ? attn8_cfg::CTAS_PER_SM_SPLIT : attn8_cfg::CTAS_PER_SM)
+template <int POLY, bool SPLIT = false, int DS = 1>
+__global__ void __launch_bounds__(attn8_cfg::NUM_THREADS,
+                                  (SPLIT || DS == 2) ? attn8_cfg::CTAS_PER_SM_SPLIT : attn8_cfg::CTAS_PER_SM)
 attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                         const AttnParams p) {
   using namespace attn8_cfg;
   constexpr float LOG2E = attn_cfg::LOG2E;
-  constexpr int NP = SPLIT ? 2 : 1;            // operand parts: hi (+ lo)
+  static_assert(!(SPLIT && DS == 2), "fp32x3 operands and two-slot heads are not combined");
+  constexpr int NP = (SPLIT || DS == 2) ? 2 : 1;  // operand tiles per Q / K / V: hi (+ lo), or slot 0 (+ slot 1)
+  constexpr int HEAD_COLS = HEAD_DIM * DS;        // columns of one head in qkv / ctx
+  constexpr int TCOLS = DS == 2 ? TMEM_COLS_WIDE : TMEM_COLS;
+  constexpr int SBUF = DS == 2 ? 2 : 1;           // S buffers (block g uses buffer g % SBUF, g = running block count)
   constexpr int QB = NP * Q_BYTES;             // Q tile(s) of one work item
   constexpr int KB = NP * KV_BYTES;            // K tile(s) / V tile(s) of one stage
   extern __shared__ uint8_t smem_raw[];
@@ -103,11 +117,11 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* q_empty = bars + 1;    // [1] MMA -> TMA (every QK^T of the tile has completed)
   uint64_t* kv_full = bars + 2;    // [2] TMA -> MMA
   uint64_t* kv_empty = bars + 4;   // [2] MMA -> TMA (2 arrivals: K released by QK^T, V by P.V)
-  uint64_t* s_full = bars + 6;     // [1] MMA -> softmax: S_j written (and P.V(j-1) accumulated)
-  uint64_t* p_full = bars + 7;     // [1] softmax -> MMA: P_j stored (128 arrivals)
-  uint64_t* o_full = bars + 8;     // [1] MMA -> softmax: last P.V of the tile accumulated
-  uint64_t* pv_done = bars + 9;    // [1] ESMB200_ATTN8_SAFE_WAR only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars + 6;     // [SBUF] MMA -> softmax: S_j written (DS 1: and P.V(j-1) accumulated)
+  uint64_t* p_full = bars + 8;     // [1] softmax -> MMA: P_j stored (128 arrivals)
+  uint64_t* o_full = bars + 9;     // [1] MMA -> softmax: last P.V of the tile accumulated
+  uint64_t* pv_done = bars + 10;   // [1] DS 2: one completion per P.V (reference-max raise); ESMB200_ATTN8_SAFE_WAR
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const uint32_t warp = threadIdx.x / 32;
   const uint32_t lane = threadIdx.x % 32;
@@ -123,14 +137,15 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 2);
     }
-    mbar_init(s_full, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_alloc(tmem_slot, TCOLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -139,7 +154,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   pdl_launch_dependents();
   pdl_wait();  // everything below reads the previous kernel's output (qkv, key bits) or writes ctx
   const uint32_t tmem_s = *tmem_slot;  // P_j occupies the first 32 columns of S_j
-  const uint32_t tmem_o = tmem_s + 64;
+  const uint32_t tmem_o = tmem_s + 64 * SBUF;
 
   auto n_blocks = [&](int w) -> int {
     const int b = w / (nqt * p.H);
@@ -155,21 +170,22 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (nblk == 0) continue;
         const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
         const int row_base = (b / p.cols) * p.T;
-        const int x0 = (b % p.cols) * 3 * p.E + h * HEAD_DIM;
+        const int x0 = (b % p.cols) * 3 * p.E + h * HEAD_COLS;
+        const int part_off = SPLIT ? p.lo_off : HEAD_DIM;  // column distance of the second operand tile
         mbar_wait_relaxed(q_empty, (tq & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, QB);
 #pragma unroll
         for (int part = 0; part < NP; ++part)
-          tma_load_2d(smem_q + part * Q_BYTES, &tmap_q, q_full, x0 + part * p.lo_off, row_base + qt * BLOCK_Q);
+          tma_load_2d(smem_q + part * Q_BYTES, &tmap_q, q_full, x0 + part * part_off, row_base + qt * BLOCK_Q);
         for (int i = 0; i < nblk; ++i, ++g) {
           const uint32_t s = g % KV_STAGES;
           mbar_wait_relaxed(&kv_empty[s], ((g / KV_STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * KB);
 #pragma unroll
           for (int part = 0; part < NP; ++part) {
-            tma_load_2d(smem_k + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E + part * p.lo_off,
+            tma_load_2d(smem_k + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + p.E + part * part_off,
                         row_base + i * BLOCK_KV);
-            tma_load_2d(smem_v + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E + part * p.lo_off,
+            tma_load_2d(smem_v + s * KB + part * KV_BYTES, &tmap_kv, &kv_full[s], x0 + 2 * p.E + part * part_off,
                         row_base + i * BLOCK_KV);
           }
         }
@@ -182,15 +198,17 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 64, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, true);
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q), 1024, 0);
-      const uint64_t qdesc_lo = umma_smem_desc_sw128(smem_u32(smem_q + Q_BYTES), 1024, 0);  // SPLIT only
+      const uint64_t qdesc_lo = umma_smem_desc_sw128(smem_u32(smem_q + Q_BYTES), 1024, 0);  // SPLIT: lo; DS 2: slot 1
       uint32_t g = 0, tq = 0, np = 0;
       auto issue_qk = [&](uint32_t gg, bool last) {
         const uint32_t s = gg % KV_STAGES;
         mbar_wait(&kv_full[s], (gg / KV_STAGES) & 1);
         tc_fence_after();
         const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * KB), 1024, 0);
+        const uint32_t sb = gg % SBUF;
+        const uint32_t tmem_sb = tmem_s + sb * 64;
 #pragma unroll
-        for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
         if constexpr (SPLIT) {  // + q_lo k_hi + q_hi k_lo
           const uint64_t kdesc_lo = umma_smem_desc_sw128(smem_u32(smem_k + s * KB + KV_BYTES), 1024, 0);
 #pragma unroll
@@ -198,7 +216,12 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
           for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc_lo + 2 * k, idesc_qk, 1u);
         }
-        tc_commit(s_full);
+        if constexpr (DS == 2) {  // + q[slot 1] . k[slot 1]
+          const uint64_t kdesc1 = umma_smem_desc_sw128(smem_u32(smem_k + s * KB + KV_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc_lo + 2 * k, kdesc1 + 2 * k, idesc_qk, 1u);
+        }
+        tc_commit(&s_full[sb]);
         tc_commit(&kv_empty[s]);
         if (last) tc_commit(q_empty);  // every QK^T of this tile has been issued: Q may be reloaded when they finish
       };
@@ -209,12 +232,16 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         issue_qk(g, nblk == 1);
         for (int j = 0; j < nblk; ++j, ++g, ++np) {
           const uint32_t s = g % KV_STAGES;
+          if constexpr (DS == 2) {  // S_{j+1} is produced while the softmax warps work on S_j
+            if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
+          }
           mbar_wait(p_full, np & 1);  // P_j stored (and, on the first block of a tile, the previous O read out)
           tc_fence_after();
+          [[maybe_unused]] const uint32_t tmem_p = tmem_s + (g % SBUF) * 64;
           const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KB), 1024, 8192);
 #pragma unroll
           for (int k = 0; k < BLOCK_KV / 16; ++k)
-            umma_ts(tmem_o, tmem_s + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            umma_ts(tmem_o, tmem_p + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
           if constexpr (SPLIT) {  // + p_lo v_hi + p_hi v_lo (P_lo lives in columns [32,64) of the S buffer)
             const uint64_t vdesc_lo = umma_smem_desc_sw128(smem_u32(smem_v + s * KB + KV_BYTES), 1024, 8192);
 #pragma unroll
@@ -222,14 +249,27 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #pragma unroll
             for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(tmem_o, tmem_s + 8 * k, vdesc_lo + 128 * k, idesc_pv, 1u);
           }
+          if constexpr (DS == 2) {  // O[:, 64:128] += P . v[slot 1]
+            const uint64_t vdesc1 = umma_smem_desc_sw128(smem_u32(smem_v + s * KB + KV_BYTES), 1024, 8192);
+#pragma unroll
+            for (int k = 0; k < BLOCK_KV / 16; ++k)
+              umma_ts(tmem_o + 64, tmem_p + 8 * k, vdesc1 + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
           tc_commit(&kv_empty[s]);
+          if constexpr (DS == 2) tc_commit(pv_done);
 #ifdef ESMB200_ATTN8_SAFE_WAR
-          tc_commit(pv_done);
-          mbar_wait(pv_done, np & 1);
-          tc_fence_after();
+          if constexpr (DS == 1) {
+            tc_commit(pv_done);
+            mbar_wait(pv_done, np & 1);
+            tc_fence_after();
+          }
 #endif
-          if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
-          else tc_commit(o_full);
+          if constexpr (DS == 2) {
+            if (j + 1 == nblk) tc_commit(o_full);
+          } else {
+            if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
+            else tc_commit(o_full);
+          }
         }
         ++tq;
       }
@@ -239,7 +279,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t quarter = warp % 4;
     const uint32_t row_local = quarter * 32 + lane;
     const uint32_t lane_addr = (quarter * 32u) << 16;
-    const uint32_t ts = tmem_s + lane_addr;
+    const uint32_t ts0 = tmem_s + lane_addr;
     uint32_t ns = 0, nt = 0;  // S blocks / tiles consumed so far (barrier phases)
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int qt = w % nqt, h = (w / nqt) % p.H, b = w / (nqt * p.H);
@@ -253,7 +293,9 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
       for (int j = 0; j < nblk; ++j, ++ns) {
         const uint2 kw2 = __ldg(reinterpret_cast<const uint2*>(kb_ptr + j * 2));
         const uint32_t kw[2] = {kw2.x, kw2.y};
-        mbar_wait(s_full, ns & 1);
+        const uint32_t sb = ns % SBUF;
+        const uint32_t ts = ts0 + sb * 64;
+        mbar_wait(&s_full[sb], (ns / SBUF) & 1);
         tc_fence_after();
         if (!seeded) {  // uniform over the CTA: the key mask is per sequence
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -323,8 +365,12 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const float m_new = fmaxf(m_ref, bmax);
           const float alpha = ex2_approx((m_ref - m_new) * LOG2E);
           if (j > 0) {
+            if constexpr (DS == 2) {  // P.V(j-1) = completion ns-1 of pv_done; P.V(j-2) finished before QK^T(j) did
+              mbar_wait(pv_done, (ns - 1) & 1);
+              tc_fence_after();
+            }
 #pragma unroll 1
-            for (int q8 = 0; q8 < 4; ++q8) {
+            for (int q8 = 0; q8 < 4 * DS; ++q8) {
               uint32_t ov[16];
               tmem_ld_32x32b_x16(tmem_o + lane_addr + q8 * 16, ov);
               tmem_wait_ld();
@@ -349,54 +395,61 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         l_run += rsum;
       }
 
-      // ---- tile epilogue: O / l -> ctx
-      uint32_t outv[32];
-      [[maybe_unused]] uint32_t outl[32];  // SPLIT: lo halves of the context
+      // ---- tile epilogue: O / l -> ctx (one 64-column slot at a time)
+      float inv = 0.f;
       if (nblk > 0) {
         mbar_wait(o_full, nt & 1);
         ++nt;
         tc_fence_after();
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      }
+      if (t < p.T && p.row_max != nullptr) {
+        const size_t si = ((size_t)b * p.H + h) * p.T + t;
+        p.row_max[si] = m_ref;
+        p.row_sum[si] = l_run;
+      }
+      const size_t pitch = SPLIT ? 2 * (size_t)p.E : (size_t)p.E;  // SPLIT: ctx [M, 2E] = hi | lo
+      uint4* dst0 = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * pitch + h * HEAD_COLS);
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t ov[32];
-          tmem_ld_32x32b_x32(tmem_o + lane_addr + hlf * 32, ov);
-          tmem_wait_ld_dep(ov);
+      for (int slot = 0; slot < DS; ++slot) {
+        uint32_t outv[32];
+        [[maybe_unused]] uint32_t outl[32];  // SPLIT: lo halves of the context
+        if (nblk > 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float y0 = __uint_as_float(ov[2 * i]) * inv, y1 = __uint_as_float(ov[2 * i + 1]) * inv;
-            const __half2 h2 = __floats2half2_rn(y0, y1);
-            outv[hlf * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
-            if constexpr (SPLIT) {
-              const float2 f = __half22float2(h2);
-              outl[hlf * 16 + i] = pack_half2(y0 - f.x, y1 - f.y);
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_addr + slot * 64 + hlf * 32, ov);
+            tmem_wait_ld_dep(ov);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float y0 = __uint_as_float(ov[2 * i]) * inv, y1 = __uint_as_float(ov[2 * i + 1]) * inv;
+              const __half2 h2 = __floats2half2_rn(y0, y1);
+              outv[hlf * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
+              if constexpr (SPLIT) {
+                const float2 f = __half22float2(h2);
+                outl[hlf * 16 + i] = pack_half2(y0 - f.x, y1 - f.y);
+              }
             }
           }
-        }
-        tc_fence_before();
-      } else {
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          outv[i] = 0u;
-          if constexpr (SPLIT) outl[i] = 0u;
+          for (int i = 0; i < 32; ++i) {
+            outv[i] = 0u;
+            if constexpr (SPLIT) outl[i] = 0u;
+          }
+        }
+        if (t < p.T) {
+          uint4* dst = dst0 + slot * 8;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
+          if constexpr (SPLIT) {
+            uint4* dl = dst + p.E / 8;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) dl[v] = make_uint4(outl[4 * v], outl[4 * v + 1], outl[4 * v + 2], outl[4 * v + 3]);
+          }
         }
       }
-      if (t < p.T) {
-        if (p.row_max != nullptr) {
-          const size_t si = ((size_t)b * p.H + h) * p.T + t;
-          p.row_max[si] = m_ref;
-          p.row_sum[si] = l_run;
-        }
-        const size_t pitch = SPLIT ? 2 * (size_t)p.E : (size_t)p.E;  // SPLIT: ctx [M, 2E] = hi | lo
-        uint4* dst = reinterpret_cast<uint4*>(p.ctx + ((size_t)(row_base + t) * p.cols + b % p.cols) * pitch + h * HEAD_DIM);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) dst[v] = make_uint4(outv[4 * v], outv[4 * v + 1], outv[4 * v + 2], outv[4 * v + 3]);
-        if constexpr (SPLIT) {
-          uint4* dl = dst + p.E / 8;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) dl[v] = make_uint4(outl[4 * v], outl[4 * v + 1], outl[4 * v + 2], outl[4 * v + 3]);
-        }
-      }
+      if (nblk > 0) tc_fence_before();  // O has been read: the arrival on p_full of the next tile's first block orders it
     }
   }
 
@@ -404,22 +457,23 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_s, TMEM_COLS);
+    tmem_dealloc(tmem_s, TCOLS);
   }
 }
 
-template <int POLY, bool SPLIT = false>
+template <int POLY, bool SPLIT = false, int DS = 1>
 inline cudaError_t launch_attention_v8_poly(const CUtensorMap& tmap_q, const CUtensorMap& tmap_kv, const AttnParams& p,
                                             int num_sms, cudaStream_t stream) {
   using namespace attn8_cfg;
-  constexpr int smem = SPLIT ? SMEM_BYTES_SPLIT : SMEM_BYTES;
-  cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel_v8<POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem);
+  constexpr bool two = SPLIT || DS == 2;
+  constexpr int smem = two ? SMEM_BYTES_SPLIT : SMEM_BYTES;
+  auto kern = attention_fwd_kernel_v8<POLY, SPLIT, DS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
-  const long long cap = (long long)(SPLIT ? CTAS_PER_SM_SPLIT : CTAS_PER_SM) * num_sms;
+  const long long cap = (long long)(two ? CTAS_PER_SM_SPLIT : CTAS_PER_SM) * num_sms;
   const int grid = (int)(total < cap ? total : cap);
-  return launch_pdl(attention_fwd_kernel_v8<POLY, SPLIT>, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, p);
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, p);
 }
 
 }  // namespace esmb200

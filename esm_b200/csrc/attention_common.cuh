@@ -11,7 +11,7 @@
 namespace esmb200 {
 
 struct AttnParams {
-  int B, T, H, E;           // E = H * 64
+  int B, T, H, E;           // E = H * 64 * slots: width of q, of k, of v and of ctx
   const uint32_t* keybits;  // [B, words]: bit i of word w set <=> key 32*w+i is attendable (not pad, < T)
   const int* kvlen;         // [B]: 1 + index of the last attendable key (0 if none)
   int words;                // words per sequence, multiple of 4
@@ -19,6 +19,7 @@ struct AttnParams {
   float* row_max;           // optional [B,H,T]: final softmax row max (of the scaled scores) ...
   float* row_sum;           // optional [B,H,T]: ... and row sum of exp(s - max), for attention_probs_kernel
   int lo_off = 0;           // fp32x3 precision: column offset (elements) of the lo halves in qkv [M, 6E] (= 3E)
+  int slots = 1;            // 64-wide column slots per head: 1 (head_dim <= 64) or 2 (head_dim <= 128); E = H * 64 * slots
   int cols = 1;             // sequence s = (s / cols, s % cols) of a [B/cols, T, cols, 3E] tensor
                             // (MSA column attention: the T tokens of a sequence are `cols` rows apart)
 };

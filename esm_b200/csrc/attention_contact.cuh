@@ -1,4 +1,4 @@
-// esm_b200 — need_head_weights + return_contacts in ONE pass (sm_100a, head_dim 64): the attention probabilities of a
+// esm_b200 — need_head_weights + return_contacts in ONE pass (sm_100a, head_dim <= 64, or <= 128 with DS = 2): the attention probabilities of a
 // layer are written to the stacked [B,L,H,T,T] result AND folded into the contact head's accumulators while they are
 // still in registers, so the 4*B*L*H*T^2-byte stack (24 GB at BASELINE.json configs[3]) is written once and never read
 // back.  r01 / attention_probs.cuh + contact_accumulate_kernel wrote it and re-read it (17 % + 14 % of configs[3]).
@@ -26,7 +26,8 @@
 namespace esmb200 {
 
 struct ContactFuseParams {
-  int B, T, H, E;            // E = 64 * H
+  int B, T, H, E;            // E = 64 * slots * H
+  int slots = 1;             // 64-wide column slots per head (2: head_dim <= 128, S_h sums both slots)
   const uint32_t* keybits;   // [B, words]
   const int* kvlen;          // [B]
   int words;
@@ -50,25 +51,29 @@ constexpr int NUM_THREADS = 544;      // warps 0-15: thread = (query row, 32-key
 constexpr int STAGES = 2;
 constexpr int TILE_BYTES = attn_cfg::TILE_BYTES;
 constexpr int TMEM_COLS = 256;        // S double buffer
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 16 * 32 * 33 * 4 /*transpose*/ +
-                           128 * 4 /*row keep flags*/;
+constexpr int smem_bytes(int ds) {  // ds operand tiles per Q and per K stage
+  return STAGES * 2 * ds * TILE_BYTES + 1024 /*align*/ + 128 /*barriers*/ + 16 * 32 * 33 * 4 /*transpose*/ +
+         128 * 4 /*row keep flags*/;
+}
 }  // namespace cfuse_cfg
 
+template <int DS>
 __global__ void __launch_bounds__(cfuse_cfg::NUM_THREADS, 1)
 attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const ContactFuseParams p) {
   using namespace cfuse_cfg;
   constexpr float LOG2E = attn_cfg::LOG2E;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                             // [STAGES]
-  uint8_t* smem_k = smem + STAGES * TILE_BYTES;       // [STAGES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * TILE_BYTES);
+  constexpr int STAGE_BYTES = DS * TILE_BYTES;        // Q (or K) tiles of one head: one per 64-wide slot
+  uint8_t* smem_q = smem;                             // [STAGES][DS]
+  uint8_t* smem_k = smem + STAGES * STAGE_BYTES;      // [STAGES][DS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * STAGE_BYTES);
   uint64_t* full = bars;         // [2] TMA -> MMA
   uint64_t* empty = bars + 2;    // [2] MMA done with the stage -> TMA
   uint64_t* s_full = bars + 4;   // [2] MMA -> softmax
   uint64_t* s_free = bars + 6;   // [2] softmax -> MMA (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * TILE_BYTES + 128);  // [16][32*33]
+  float* tiles = reinterpret_cast<float*>(smem + STAGES * 2 * STAGE_BYTES + 128);  // [16][32*33]
   float* rowkeep = tiles + 16 * 32 * 33;                                          // [128]
 
   const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -104,9 +109,13 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
       constexpr uint32_t idesc = umma_idesc_f16(128, 128, false);
       auto load = [&](int h) {
         const int s = h & 1;
-        mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
-        tma_load_2d(smem_q + s * TILE_BYTES, &tmap_qkv, &full[s], h * 64, row_base + q0);
-        tma_load_2d(smem_k + s * TILE_BYTES, &tmap_qkv, &full[s], p.E + h * 64, row_base + k0);
+        mbar_arrive_expect_tx(&full[s], 2 * STAGE_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < DS; ++sl) {
+          tma_load_2d(smem_q + s * STAGE_BYTES + sl * TILE_BYTES, &tmap_qkv, &full[s], (h * DS + sl) * 64, row_base + q0);
+          tma_load_2d(smem_k + s * STAGE_BYTES + sl * TILE_BYTES, &tmap_qkv, &full[s], p.E + (h * DS + sl) * 64,
+                      row_base + k0);
+        }
       };
       load(0);
       if (p.H > 1) load(1);
@@ -116,10 +125,13 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
         mbar_wait(&full[s], ph);
         if (h >= 2) mbar_wait(&s_free[s], ((h - 2) >> 1) & 1);  // the softmax threads have read S of head h-2
         tc_fence_after();
-        const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q + s * TILE_BYTES), 1024, 0);
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * TILE_BYTES), 1024, 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_s + s * 128, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0);
+        for (int sl = 0; sl < DS; ++sl) {
+          const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q + s * STAGE_BYTES + sl * TILE_BYTES), 1024, 0);
+          const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * STAGE_BYTES + sl * TILE_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_s + s * 128, qdesc + 2 * k, kdesc + 2 * k, idesc, (sl | k) != 0);
+        }
         tc_commit(&s_full[s]);
         tc_commit(&empty[s]);
         if (h + 2 < p.H) {
@@ -229,14 +241,21 @@ attention_probs_contact_kernel(const __grid_constant__ CUtensorMap tmap_qkv, con
   }
 }
 
-inline cudaError_t launch_attention_probs_contact(const CUtensorMap& tmap_qkv, const ContactFuseParams& p,
-                                                  cudaStream_t stream) {
+template <int DS>
+inline cudaError_t launch_attention_probs_contact_ds(const CUtensorMap& tmap_qkv, const ContactFuseParams& p,
+                                                     cudaStream_t stream) {
   using namespace cfuse_cfg;
-  cudaError_t e = cudaFuncSetAttribute(attention_probs_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES);
+  constexpr int smem = smem_bytes(DS);
+  cudaError_t e = cudaFuncSetAttribute(attention_probs_contact_kernel<DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid((p.T + BLOCK - 1) / BLOCK, (p.T + BLOCK - 1) / BLOCK, p.B);
-  return launch_pdl(attention_probs_contact_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_qkv, p);
+  return launch_pdl(attention_probs_contact_kernel<DS>, grid, dim3(NUM_THREADS), smem, stream, tmap_qkv, p);
+}
+
+inline cudaError_t launch_attention_probs_contact(const CUtensorMap& tmap_qkv, const ContactFuseParams& p,
+                                                  cudaStream_t stream) {
+  return p.slots == 2 ? launch_attention_probs_contact_ds<2>(tmap_qkv, p, stream)
+                      : launch_attention_probs_contact_ds<1>(tmap_qkv, p, stream);
 }
 
 }  // namespace esmb200

@@ -21,6 +21,7 @@ struct ProbsParams {
   long long batch_stride;
   int zero_pad_rows;  // 1: rows of padded query tokens are written as zeros (ESM2.forward's stacked result)
   int lo_off;         // fp32x3 precision: column offset of the lo halves in qkv [M, 6E] (0 = plain fp16 operands)
+  int slots = 1;      // 2: head_dim <= 128, a head is two adjacent 64-wide column slots (E = H * 128)
 };
 
 namespace probs_cfg {
@@ -31,14 +32,16 @@ constexpr int SMEM_BYTES_SPLIT = 4 * attn_cfg::TILE_BYTES + 1024 + 64 + 4 * 32 *
 constexpr int SMEM_BYTES = 2 * attn_cfg::TILE_BYTES + 1024 + 64 + 4 * 32 * 33 * 4;  // + per-warp transpose tiles
 }  // namespace probs_cfg
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(probs_cfg::NUM_THREADS, SPLIT ? 2 : 4)
+// MODE 0: fp16 operands, head_dim <= 64 | 1 (SPLIT): fp32x3 hi|lo operands | 2: two 64-wide slots per head
+template <int MODE>
+__global__ void __launch_bounds__(probs_cfg::NUM_THREADS, MODE ? 2 : 4)
 attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const ProbsParams p) {
   using namespace attn_cfg;
   using namespace probs_cfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr bool SPLIT = MODE == 1;
+  constexpr int NP = MODE ? 2 : 1;
   uint8_t* smem_q = smem;                    // [hi | lo]
   uint8_t* smem_k = smem + NP * TILE_BYTES;  // [hi | lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * NP * TILE_BYTES);
@@ -71,10 +74,11 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
 
   if (live && threadIdx.x == 0) {
     mbar_arrive_expect_tx(ld_full, 2 * NP * TILE_BYTES);
+    const int hc = h * HEAD_DIM * (MODE == 2 ? 2 : 1), po = MODE == 2 ? HEAD_DIM : p.lo_off;
 #pragma unroll
     for (int part = 0; part < NP; ++part) {
-      tma_load_2d(smem_q + part * TILE_BYTES, &tmap_qkv, ld_full, h * HEAD_DIM + part * p.lo_off, row_base + q0);
-      tma_load_2d(smem_k + part * TILE_BYTES, &tmap_qkv, ld_full, p.E + h * HEAD_DIM + part * p.lo_off, row_base + k0);
+      tma_load_2d(smem_q + part * TILE_BYTES, &tmap_qkv, ld_full, hc + part * po, row_base + q0);
+      tma_load_2d(smem_k + part * TILE_BYTES, &tmap_qkv, ld_full, p.E + hc + part * po, row_base + k0);
     }
     mbar_wait(ld_full, 0);
     tc_fence_after();
@@ -90,6 +94,12 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
       for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qlo + 2 * k, kdesc + 2 * k, idesc_qk, 1u);
 #pragma unroll
       for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, klo + 2 * k, idesc_qk, 1u);
+    }
+    if constexpr (MODE == 2) {  // + q[slot 1] . k[slot 1]
+      const uint64_t q1 = umma_smem_desc_sw128(smem_u32(smem_q + TILE_BYTES), 1024, 0);
+      const uint64_t k1 = umma_smem_desc_sw128(smem_u32(smem_k + TILE_BYTES), 1024, 0);
+#pragma unroll
+      for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, q1 + 2 * k, k1 + 2 * k, idesc_qk, 1u);
     }
     tc_commit(mma_done);
   }
@@ -150,19 +160,20 @@ attention_probs_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Probs
   }
 }
 
-inline cudaError_t launch_attention_probs(const CUtensorMap& tmap_qkv, const ProbsParams& p, cudaStream_t stream) {
+template <int MODE>
+inline cudaError_t launch_attention_probs_mode(const CUtensorMap& tmap_qkv, const ProbsParams& p, cudaStream_t stream) {
   using namespace probs_cfg;
+  constexpr int smem = MODE ? SMEM_BYTES_SPLIT : SMEM_BYTES;
   dim3 grid((p.T + BLOCK_KV - 1) / BLOCK_KV, (p.T + BLOCK_Q - 1) / BLOCK_Q, p.B * p.H);
-  if (p.lo_off > 0) {
-    cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SMEM_BYTES_SPLIT);
-    if (e != cudaSuccess) return e;
-    return launch_pdl(attention_probs_kernel<true>, grid, dim3(NUM_THREADS), SMEM_BYTES_SPLIT, stream, tmap_qkv, p);
-  }
-  cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(attention_probs_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return launch_pdl(attention_probs_kernel<false>, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, tmap_qkv, p);
+  return launch_pdl(attention_probs_kernel<MODE>, grid, dim3(NUM_THREADS), smem, stream, tmap_qkv, p);
+}
+
+inline cudaError_t launch_attention_probs(const CUtensorMap& tmap_qkv, const ProbsParams& p, cudaStream_t stream) {
+  if (p.slots == 2) return launch_attention_probs_mode<2>(tmap_qkv, p, stream);
+  if (p.lo_off > 0) return launch_attention_probs_mode<1>(tmap_qkv, p, stream);
+  return launch_attention_probs_mode<0>(tmap_qkv, p, stream);
 }
 
 }  // namespace esmb200

@@ -98,34 +98,40 @@ inline cudaError_t launch_layernorm(const float* x, const float* gamma, const fl
   return launch_pdl(layernorm_rows_kernel<40, OUT>, g, b, 0, stream, x, gamma, beta, out, M, E, eps);
 }
 
-// One block per sequence: counts <mask>/<pad>, then writes the scaled embedding rows.
+// grid (row chunks, B): every block counts the <mask>/<pad> tokens of its sequence (T 8-byte reads, cheaper than a
+// separate pass) and writes the scaled embedding rows of its chunk.  (One block per sequence left a 32-sequence batch —
+// the per-GPU share at 8 GPUs — on 32 SMs: 0.6 ms, 1 % of that step.)
 __global__ void __launch_bounds__(256)
 embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ table, float* __restrict__ x, int T,
                     int E, int padding_idx, int mask_idx, int token_dropout) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const int64_t* tok = tokens + (size_t)b * T;
   __shared__ int s_cnt[2];
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  int n_mask = 0, n_pad = 0;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const int64_t v = tok[t];
-    n_mask += (v == mask_idx);
-    n_pad += (v == padding_idx);
+  if (token_dropout) {
+    int n_mask = 0, n_pad = 0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const int64_t v = tok[t];
+      n_mask += (v == mask_idx);
+      n_pad += (v == padding_idx);
+    }
+    n_mask = (int)warp_sum((float)n_mask);
+    n_pad = (int)warp_sum((float)n_pad);
+    if (threadIdx.x % 32 == 0) {
+      atomicAdd(&s_cnt[0], n_mask);
+      atomicAdd(&s_cnt[1], n_pad);
+    }
+    __syncthreads();
   }
-  n_mask = (int)warp_sum((float)n_mask);
-  n_pad = (int)warp_sum((float)n_pad);
-  if (threadIdx.x % 32 == 0) {
-    atomicAdd(&s_cnt[0], n_mask);
-    atomicAdd(&s_cnt[1], n_pad);
-  }
-  __syncthreads();
   // esm2.py:86-92: x.masked_fill_(mask, 0); x = x * (1 - 0.15*0.8) / (1 - n_mask / src_length)
   // (python evaluates 1 - 0.15*0.8 in double, the tensor ops run in fp32: multiply first, then divide)
   const float keep = (float)(1.0 - 0.15 * 0.8);
   const float denom = 1.0f - (float)s_cnt[0] / (float)(T - s_cnt[1]);
   const int nvec = E / 4;
-  for (int i = threadIdx.x; i < T * nvec; i += blockDim.x) {
+  const int rows = (T + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * rows, t1 = min(T, t0 + rows);
+  for (int i = t0 * nvec + threadIdx.x; i < t1 * nvec; i += blockDim.x) {
     const int t = i / nvec, c = i % nvec;
     const int64_t v = tok[t];
     float4 e = __ldg(reinterpret_cast<const float4*>(table + (size_t)v * E) + c);
@@ -160,25 +166,48 @@ __global__ void key_bits_kernel(const uint8_t* __restrict__ pad_mask, uint32_t* 
 }
 
 // Per-sequence mean over residues (scripts/extract.py:116-119: representations[i, 1 : len+1].mean(0)).
-// grid (ceil(E/256), B); thread = one column, rows streamed with coalesced 1 KB warp-rows.
+// grid (ceil(E/128), B), block 256 = 8 row lanes x 32 float4 columns: row lane r sums the residues t = r (mod 8) of its
+// 128 columns (512-byte coalesced warp rows, 4 independent accumulators), the 8 partial sums are combined through shared
+// memory in a fixed order (deterministic).  E % 4 == 0.
 __global__ void __launch_bounds__(256)
 mean_pool_kernel(const float* __restrict__ x, const int* __restrict__ lengths, float* __restrict__ out, int T, int E) {
   const int b = blockIdx.y;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= E) return;
+  const int lane = threadIdx.x % 32, rl = threadIdx.x / 32;
+  const int col = blockIdx.x * 128 + lane * 4;
+  __shared__ float4 part[8][32];
   int n = lengths[b];
   n = n < 0 ? 0 : (n > T - 1 ? T - 1 : n);
-  const float* xp = x + ((size_t)b * T + 1) * E + col;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int t = 0;
-  for (; t + 4 <= n; t += 4) {
-    a0 += xp[(size_t)(t + 0) * E];
-    a1 += xp[(size_t)(t + 1) * E];
-    a2 += xp[(size_t)(t + 2) * E];
-    a3 += xp[(size_t)(t + 3) * E];
+  float4 a[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < E) {
+    const float* xp = x + ((size_t)b * T + 1) * E + col;
+    int t = rl;
+    for (; t + 24 < n; t += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 v = *reinterpret_cast<const float4*>(xp + (size_t)(t + 8 * u) * E);
+        a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
+      }
+    }
+    for (; t < n; t += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + (size_t)t * E);
+      a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+    }
   }
-  for (; t < n; ++t) a0 += xp[(size_t)t * E];
-  out[(size_t)b * E + col] = ((a0 + a1) + (a2 + a3)) / (float)n;
+  part[rl][lane] = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                               (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w));
+  __syncthreads();
+  if (rl == 0 && col < E) {
+    float4 s = part[0][lane];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      const float4 v = part[r][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.0f / (float)n;  // n == 0: inf * 0 = NaN like the reference's mean over an empty slice
+    *reinterpret_cast<float4*>(out + (size_t)b * E + col) = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+  }
 }
 
 __global__ void convert_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
@@ -200,16 +229,20 @@ __global__ void convert_f32_split_kernel(const float* __restrict__ src, __half* 
   }
 }
 
-// head_dim < 64: every head's projection rows go to a zero-padded 64-wide slot, first half of the head at slot
-// positions [0, d/2), second half at [32, 32 + d/2) so that the RoPE epilogue's (j, j+32) pairing reproduces the
-// reference's (j, j+d/2) rotate-half pairs (rotary_embedding.py:11-20).  dst must be zero-filled by the caller.
-__device__ __forceinline__ int head_slot(int n, int d) {  // projection output index n = h*d + j -> h*64 + slot(j)
-  const int h = n / d, j = n % d;
-  return h * 64 + (j < d / 2 ? j : 32 + (j - d / 2));
+// head_dim != 64: every head's projection rows go to zero-padded 64-wide *slots* — one per head for d <= 64, two for
+// 64 < d <= 128 (ESM-2 15B).  The reference's rotate-half pair p = (j, j + d/2), p < d/2 (rotary_embedding.py:11-20),
+// lands in slot p / 32 at positions (p % 32, 32 + p % 32), so the RoPE epilogue's fixed (c, c + 32) pairing inside a
+// 64-column group reproduces it with table column p, and q.k / P.v — sums over the head dimension — do not care about the
+// order.  dst must be zero-filled by the caller.
+__device__ __forceinline__ int head_slot(int n, int d) {  // projection output index n = h*d + j -> attention-side column
+  const int h = n / d, j = n % d, half = d / 2;
+  const int pr = j < half ? j : j - half;
+  const int slots = d > 64 ? 2 : 1;
+  return (h * slots + pr / 32) * 64 + (pr % 32) + (j < half ? 0 : 32);
 }
 // split != 0: fp32x3 operand layout, row pitch 2K with the lo halves K columns to the right
 __global__ void pack_head_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ dst,
-                                      float* __restrict__ bdst, int E, int d, int split) {  // w [E,E] -> dst [64*H, E]
+                                      float* __restrict__ bdst, int E, int d, int split) {  // w [E,E] -> dst [Ea, E]
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)E * E) return;
   const int n = (int)(i / E), k = (int)(i % E);

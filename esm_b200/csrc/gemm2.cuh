@@ -189,26 +189,33 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int iter = 0;
     [[maybe_unused]] float rc[32], rs[32];  // EPI_QKV_ROPE: cos / sin of this thread's row
     [[maybe_unused]] int rope_blk = -1;
+    [[maybe_unused]] int rope_row = 0;      // row of the current tile (set per tile)
+    // table columns [slot*32, slot*32 + 32) of this thread's token position -> rc / rs
+    [[maybe_unused]] auto load_rope = [&](int slot) {
+      const int t = (rope_row < p.M) ? (rope_row % p.T) : 0;
+      const int ld = p.rope_ld == 64 ? 64 : 32;
+      const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * ld + slot * 32);
+      const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * ld + slot * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
+        rc[4 * j4 + 0] = c.x; rc[4 * j4 + 1] = c.y; rc[4 * j4 + 2] = c.z; rc[4 * j4 + 3] = c.w;
+        rs[4 * j4 + 0] = sn.x; rs[4 * j4 + 1] = sn.y; rs[4 * j4 + 2] = sn.z; rs[4 * j4 + 3] = sn.w;
+      }
+    };
     for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
       const int row0 = m_blk * PAIR_M + rank * BLOCK_M;
       const int row = row0 + row_local;
+      rope_row = row;
       if constexpr (EPI == EPI_QKV_ROPE) {  // before the wait: the loads fly while the tile is still being multiplied
       // cos/sin of this thread's token position, 64 registers, reloaded only when the 256-row slab changes (tiles are
       // walked n-fastest, so once per tiles_n tiles) — r01 re-read them from L2 for every 64-column head group
       // (256 B per thread and group, long-scoreboard stalls in the shortest-K GEMM of the layer).
-      if (p.rope_cos != nullptr && m_blk != rope_blk) {
+      if (p.rope_cos != nullptr && m_blk != rope_blk && p.rope_ld != 64) {
         rope_blk = m_blk;
-        const int t = (row < p.M) ? (row % p.T) : 0;
-        const float4* cs4 = reinterpret_cast<const float4*>(p.rope_cos + (size_t)t * 32);
-        const float4* sn4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)t * 32);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 c = __ldg(cs4 + j4), sn = __ldg(sn4 + j4);
-          rc[4 * j4 + 0] = c.x; rc[4 * j4 + 1] = c.y; rc[4 * j4 + 2] = c.z; rc[4 * j4 + 3] = c.w;
-          rs[4 * j4 + 0] = sn.x; rs[4 * j4 + 1] = sn.y; rs[4 * j4 + 2] = sn.z; rs[4 * j4 + 3] = sn.w;
-        }
+        load_rope(0);
       }
       }
       mbar_wait(&tfull_bar[as], aph);
@@ -386,6 +393,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
           const int sect = col / p.E;  // 0 q, 1 k, 2 v
           const float sc = (sect == 0) ? p.q_scale : 1.0f;
+          // head_dim > 64: two 64-wide slots per head with different frequencies — reload per group (15B only)
+          if (rope && sect < 2 && p.rope_ld == 64) load_rope((col >> 6) & 1);
           tmem_wait_ld_dep(lo);  // one wait retires both loads
           reg_fence(hi);
           if (sect < 2 && rope) {

@@ -26,8 +26,10 @@ struct GemmParams {
   void* out;              // fp16 or fp32, row-major [M, ldo]
   int ldo;
   // EPI_QKV_ROPE only
-  const float* rope_cos;  // [T, 32] fp32 (angle t * inv_freq[j], j < d/2)
+  const float* rope_cos;  // [T, rope_ld] fp32 (angle t * inv_freq[j], j < d/2; further columns are padding)
   const float* rope_sin;
+  int rope_ld;            // 0 / 32: head_dim <= 64, one 64-wide slot per head; 64: head_dim <= 128, two slots per head —
+                          // the odd 64-column groups take table columns [32,64) (elementwise.cuh head_slot)
   int T;                  // tokens per sequence: position of row r is r % T
   int E;                  // embed dim: columns [0,E) = q, [E,2E) = k, [2E,3E) = v
   float q_scale;          // head_dim^-0.5

@@ -11,7 +11,8 @@ Documented deviations from the reference:
   * `TransformerLayer.forward` returns `attn=None` unless `need_head_weights=True` (the reference always computes a
     head-averaged (B,T,T) map that ESM2.forward discards, modules.py:130 / esm2.py:112-121).
   * MMA operands are fp16 (fp32 accumulate, fp32 residual stream / LayerNorm / softmax); tolerance in DESIGN.md.
-  * head_dim <= 64 (all ESM-2 checkpoints except 15B); heads narrower than 64 run in zero-padded 64-wide slots.
+  * head_dim <= 128 (every ESM-2 checkpoint); heads other than 64 wide run in zero-padded 64-wide slots (two per head
+    above 64: 15B).
 """
 from __future__ import annotations
 
@@ -60,14 +61,15 @@ class MultiheadAttention(nn.Module):
 
 
 def rope_tables(inv_freq: torch.Tensor, seq_len: int):
-    """cos/sin [T, 32] fp32 — rotary_embedding.py:53-59 (the reference's table is the first d/2 columns duplicated on
-    the last dim); columns >= d/2 (head_dim < 64) are padding the kernels never use."""
+    """cos/sin [T, 32] fp32 (head_dim <= 64) or [T, 64] (head_dim <= 128) — rotary_embedding.py:53-59 (the reference's
+    table is the first d/2 columns duplicated on the last dim); columns >= d/2 are padding the kernels never use."""
     inv_freq = inv_freq.float()
     t = torch.arange(seq_len, device=inv_freq.device).type_as(inv_freq)
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     cos, sin = freqs.cos(), freqs.sin()
-    if cos.shape[1] < 32:
-        pad = 32 - cos.shape[1]
+    width = 32 if cos.shape[1] <= 32 else 64
+    if cos.shape[1] < width:
+        pad = width - cos.shape[1]
         cos, sin = F.pad(cos, (0, pad), value=1.0), F.pad(sin, (0, pad), value=0.0)
     return cos.contiguous(), sin.contiguous()
 
@@ -94,8 +96,8 @@ class LayerBinding:
         self.attention_heads = a.num_heads
         self.head_dim = self.embed_dim // self.attention_heads
         self.ffn_embed_dim = module.fc1.weight.shape[0]
-        if self.head_dim * self.attention_heads != self.embed_dim or self.head_dim > 64 or self.head_dim % 2:
-            raise ValueError("esm_b200 supports even head_dim <= 64 (ESM-2 8M/35M/150M/650M/3B); "
+        if self.head_dim * self.attention_heads != self.embed_dim or self.head_dim > 128 or self.head_dim % 2:
+            raise ValueError("esm_b200 supports even head_dim <= 128 (every ESM-2 model); "
                              f"got embed_dim={self.embed_dim}, heads={self.attention_heads}")
         self.precision = 0  # 0 = fp16 MMA operands, 1 = "fp32x3" (esmb200.h: esmb200_layer_weights.precision)
         self._handle = None
@@ -516,8 +518,8 @@ class ESM2(nn.Module):
         embed_dim % 64 == 0."""
         if name not in self.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}")
-        if name == "fp32x3" and self.embed_dim % 64 != 0:
-            raise ValueError("fp32x3 precision needs embed_dim % 64 == 0")
+        if name == "fp32x3" and (self.embed_dim % 64 != 0 or self.embed_dim // self.attention_heads > 64):
+            raise ValueError("fp32x3 precision needs embed_dim % 64 == 0 and head_dim <= 64")
         self.precision = name
         for layer in self.layers:
             layer.precision = self.PRECISIONS[name]

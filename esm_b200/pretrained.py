@@ -7,7 +7,7 @@ key-upgrade rule as pretrained.py:164-183).  When it is not — there is no netw
 RAISE like the reference does when weights cannot be obtained; `allow_random_init=True` (benchmarks and tests) returns a
 seeded random-init model instead, with a warning and `model.random_init = True`.
 Loading is strict like pretrained.py:200-219: only `contact_head.regression.*` may be missing (with a warning).
-The 15B model (head_dim 128) raises at construction.
+The 15B model (head_dim 128) runs with two 64-wide column slots per head.
 """
 from __future__ import annotations
 

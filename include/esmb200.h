@@ -62,12 +62,13 @@ typedef struct esmb200_layer_weights {
   const float* fc1_bias;   /* fc1.bias   [F]   */
   const float* fc2_weight; /* fc2.weight [E,F] */
   const float* fc2_bias;   /* fc2.bias   [E]   */
-  int32_t head_dim;        /* 0 = E / H. Even values <= 64: 16 / 24 / 32 (ESM-2 8M / 35M / 150M) run in zero-padded
-                            * 64-wide head slots of the attention-side tensors; 64 = 650M / 3B / MSA Transformer */
+  int32_t head_dim;        /* 0 = E / H. Even values <= 128. 16 / 24 / 32 (ESM-2 8M / 35M / 150M) run in zero-padded
+                            * 64-wide head slots of the attention-side tensors; 64 = 650M / 3B / MSA Transformer;
+                            * 65..128 (15B: 128) take two slots per head and 64-column rope tables */
   int32_t precision;       /* 0 = fp16 MMA operands (default). 1 = "fp32x3": every MMA operand (activations, weights,
                             * q, k, v, P) is an fp16 hi | lo pair and every product runs hi*hi + lo*hi + hi*lo into the
                             * fp32 accumulator (22 significand bits per operand) — fp32-grade results at ~3x the tensor
-                            * work; needs E % 64 == 0; not available on the MSA axial path */
+                            * work; needs E % 64 == 0 and head_dim <= 64; not available on the MSA axial path */
 } esmb200_layer_weights;
 
 int esmb200_abi_version(void);
@@ -87,8 +88,8 @@ size_t esmb200_workspace_bytes(int32_t embed_dim, int32_t num_heads, int32_t ffn
  *     x += fc2(gelu(fc1(LN2 x)))
  *   x          fp32 [B,T,E], updated in place
  *   pad_mask   uint8/bool [B,T], nonzero = padding key (self_attn_padding_mask, esm2.py:82), or NULL
- *   rope_cos/sin fp32 [T,32]: cos/sin(t * inv_freq[j]) for j < head_dim/2 (rotary_embedding.py:47-61), built by the
- *              caller; columns >= head_dim/2 are ignored
+ *   rope_cos/sin fp32 [T,32] (head_dim <= 64) or [T,64] (head_dim <= 128): cos/sin(t * inv_freq[j]) for j < head_dim/2
+ *              (rotary_embedding.py:47-61), built by the caller; columns >= head_dim/2 are ignored
  *   attn_probs fp32 [B,H,T,T] or NULL: softmax probabilities per head (need_head_weights=True,
  *              multihead_attention.py:397-400, batch-major i.e. already transposed as esm2.py:121 does) */
 int esmb200_layer_forward(esmb200_layer* layer, float* x, const uint8_t* pad_mask, int32_t B, int32_t T,
@@ -157,6 +158,11 @@ int esmb200_gemm_qkv_f16(const void* a_f16, const void* w_qkv_f16, const float* 
 size_t esmb200_attention_scratch_bytes(int32_t B, int32_t T);
 int esmb200_attention(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, float* attn_probs, int32_t B,
                       int32_t T, int32_t H, void* scratch, void* stream);
+/* The same for head_dim 128 (esm2_t48_15B, esm/pretrained.py:390-397): qkv fp16 [B*T, 3*128*H], ctx fp16 [B*T, 128*H];
+ * a head is two adjacent 64-wide column slots, any fixed permutation of the 128 dimensions that is
+ * shared by q, k and v gives the same result. */
+int esmb200_attention128(const void* qkv_f16, const uint8_t* pad_mask, void* ctx_f16, float* attn_probs, int32_t B,
+                         int32_t T, int32_t H, void* scratch, void* stream);
 
 /* ---- MSA Transformer axial attention on qkv fp16 [B*R*C, 3E] (B alignments, R rows, C columns; q pre-scaled) ----
  * esmb200_tied_row_attention: RowSelfAttention.compute_attention_weights / compute_attention_update,

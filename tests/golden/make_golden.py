@@ -2,7 +2,7 @@
 /root/reference) on the deterministic weights/tokens of oracle/weights.py.
 
 Run in the build container only (the GPU box has no /root/reference):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 The fixtures hold tokens + reference outputs; the weights are re-created from (num_layers, E, H, seed) by
 oracle.weights.make_state_dict on whichever machine runs the tests (same torch version => same CPU generator stream;
 a checksum of the state dict is stored in the fixture and verified by the tests).
@@ -27,6 +27,8 @@ CASES = {
     "mid_L3_E256_H4": (3, 256, 4, [198, 150], 200, 1, [0, 2, 3]),
     "t6_8M_like_L6_E320_H20": (6, 320, 20, [64, 64, 64, 64], 66, 0, [6]),
     "nopad_L2_E128_H2": (2, 128, 2, [126, 126], 128, 0, [2]),
+    # head_dim 128 = esm2_t48_15B's head width (pretrained.py:390-397) at a small embedding width
+    "t48_15B_like_L2_E256_H2": (2, 256, 2, [140, 97], 142, 1, [0, 1, 2]),
 }
 
 
@@ -37,7 +39,10 @@ def checksum(sd):
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])  # optional: regenerate just the named cases
     for name, (L, E, H, lengths, total, n_mask, repr_layers) in CASES.items():
+        if only and name not in only:
+            continue
         sd = make_state_dict(L, E, H, seed=0)
         model = esm.model.esm2.ESM2(num_layers=L, embed_dim=E, attention_heads=H, alphabet="ESM-1b")
         missing = model.load_state_dict(sd, strict=True)

@@ -58,15 +58,17 @@ def test_no_cpu_fallback():
         model(tokens)
 
 
-def test_every_esm2_factory_constructs_except_15B():
-    """esm.pretrained.esm2_* (pretrained.py:344-397): head_dim 16 / 24 / 32 / 64 construct (narrow heads run in padded
-    64-wide slots); the 15B model's 128-wide heads are rejected at construction, loudly."""
+def test_every_esm2_factory_shape_constructs():
+    """esm.pretrained.esm2_* (pretrained.py:344-397): head_dim 16 / 24 / 32 / 64 / 128 construct (heads that are not 64
+    wide run in padded 64-wide slots, two per head for 15B); wider or odd heads are rejected at construction, loudly."""
     from esm_b200 import ESM2
-    for L, E, H in [(1, 320, 20), (1, 480, 20), (1, 640, 20), (1, 1280, 20)]:
+    for L, E, H in [(1, 320, 20), (1, 480, 20), (1, 640, 20), (1, 1280, 20), (1, 256, 2)]:
         m = ESM2(num_layers=L, embed_dim=E, attention_heads=H)
         assert m.layers[0].self_attn.head_dim == E // H
     with pytest.raises(ValueError):
-        ESM2(num_layers=1, embed_dim=5120, attention_heads=40)
+        ESM2(num_layers=1, embed_dim=512, attention_heads=2)   # head_dim 256
+    with pytest.raises(ValueError):
+        ESM2(num_layers=1, embed_dim=66, attention_heads=2)    # head_dim 33
 
 
 def test_state_dict_keys_match_reference_layout():

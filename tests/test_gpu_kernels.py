@@ -116,9 +116,9 @@ def test_gemm_qkv_rope(dev, B, T, H):
     torch.testing.assert_close(out.float(), ref, atol=3e-3, rtol=2e-3)
 
 
-def _attention_ref(qkv, pad, B, T, H):
-    E = 64 * H
-    y = qkv.float().view(B, T, 3, H, 64)
+def _attention_ref(qkv, pad, B, T, H, D=64):
+    E = D * H
+    y = qkv.float().view(B, T, 3, H, D)
     q, k, v = (y[:, :, i].transpose(1, 2) for i in range(3))
     s = q @ k.transpose(-1, -2)
     if pad is not None:
@@ -161,45 +161,79 @@ def test_attention_forward_and_probs(dev, B, T, H, lengths):
     assert torch.equal(ctx, ctx2)
 
 
-def test_attention_reference_max_raise(dev):
-    """Scores that keep growing along the key axis (each 128-key block beats the previous maximum by far more than
-    the lazy-rescale threshold) force the O-rescale / block-redo path; result must still be the exact softmax."""
+@pytest.mark.parametrize("B,T,H,lengths", [(1, 128, 1, None), (2, 200, 3, [200, 61]), (2, 1024, 4, [1024, 517]),
+                                            (1, 129, 2, [129])])
+def test_attention_head_dim_128(dev, B, T, H, lengths):
+    """esm2_t48_15B's head width (pretrained.py:390-397): the same contract as above on 128-wide heads (two 64-wide
+    column slots per head: QK^T sums both, P.V runs once per slot), context and probabilities."""
     L = _lib(); lib = L.load()
-    B, T, H = 1, 640, 2
-    E = 64 * H
+    E = 128 * H
+    g = torch.Generator(device="cpu").manual_seed(B * 977 + T)
+    qkv = torch.randn(B * T, 3 * E, generator=g)
+    qkv[:, :E] *= 0.35
+    qkv = qkv.half().to(dev)
+    pad = None
+    if lengths is not None:
+        pad = torch.zeros(B, T, dtype=torch.uint8)
+        for b, n in enumerate(lengths):
+            pad[b, n:] = 1
+        pad = pad.to(dev)
+    ctx = torch.full((B * T, E), float("nan"), dtype=torch.float16, device=dev)
+    probs = torch.full((B, H, T, T), float("nan"), device=dev)
+    scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
+    L.check(lib.esmb200_attention128(P(qkv), P(pad), P(ctx), P(probs), B, T, H, P(scratch), S()))
+    ref_o, ref_p = _attention_ref(qkv, pad, B, T, H, 128)
+    torch.testing.assert_close(ctx.float(), ref_o, atol=4e-3, rtol=4e-3)
+    torch.testing.assert_close(probs, ref_p, atol=2e-5, rtol=2e-4)
+    ctx2 = torch.empty_like(ctx)
+    L.check(lib.esmb200_attention128(P(qkv), P(pad), P(ctx2), None, B, T, H, P(scratch), S()))
+    assert torch.equal(ctx, ctx2)
+
+
+@pytest.mark.parametrize("D,B,H", [(64, 1, 2), (128, 1, 2), (128, 3, 40)])
+def test_attention_reference_max_raise(dev, D, B, H):
+    """Scores that keep growing along the key axis (each 128-key block beats the previous maximum by far more than
+    the lazy-rescale threshold) force the O-rescale / block-redo path; result must still be the exact softmax.
+    (D = 128: the double-buffered two-slot kernel, whose rescale waits for the previous P.V; the 3 x 40-head case keeps
+    every CTA of the GPU busy with several tiles.)"""
+    L = _lib(); lib = L.load()
+    T = 640
+    E = D * H
     g = torch.Generator(device="cpu").manual_seed(5)
     qkv = torch.randn(B * T, 3 * E, generator=g)
-    u = torch.randn(64, generator=g)
+    u = torch.randn(D, generator=g)
     u = u / u.norm() * (8.0 ** 0.5)                              # |u|^2 = 8
-    blk = (torch.arange(T).float() / 128).floor()
+    blk = (torch.arange(B * T).float() % T / 128).floor()
     for h in range(H):
-        qkv[:, h * 64:(h + 1) * 64] = u + 0.1 * torch.randn(T, 64, generator=g)
+        qkv[:, h * D:(h + 1) * D] = u + 0.1 * torch.randn(B * T, D, generator=g)
         # logits ~ 8 * 0.8 * block index: every block tops the previous maximum by ~6.4 > tau (5.5)
-        qkv[:, E + h * 64:E + (h + 1) * 64] = u * (0.8 * blk[:, None]) + 0.3 * torch.randn(T, 64, generator=g)
+        qkv[:, E + h * D:E + (h + 1) * D] = u * (0.8 * blk[:, None]) + 0.3 * torch.randn(B * T, D, generator=g)
     qkv = qkv.half().to(dev)
     ctx = torch.empty(B * T, E, dtype=torch.float16, device=dev)
     probs = torch.empty(B, H, T, T, device=dev)
     scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
-    L.check(lib.esmb200_attention(P(qkv), None, P(ctx), P(probs), B, T, H, P(scratch), S()))
-    ref_o, ref_p = _attention_ref(qkv, None, B, T, H)
+    fn = lib.esmb200_attention if D == 64 else lib.esmb200_attention128
+    L.check(fn(P(qkv), None, P(ctx), P(probs), B, T, H, P(scratch), S()))
+    ref_o, ref_p = _attention_ref(qkv, None, B, T, H, D)
     torch.testing.assert_close(ctx.float(), ref_o, atol=4e-3, rtol=4e-3)
     torch.testing.assert_close(probs, ref_p, atol=1e-4, rtol=1e-3)
 
 
-def test_attention_left_and_interior_padding_with_very_negative_scores(dev):
+@pytest.mark.parametrize("D", [64, 128])
+def test_attention_left_and_interior_padding_with_very_negative_scores(dev, D):
     """when the first key block is fully padded the reference maximum must be seeded from the first block that
     has an attendable key — with scores around -40 a reference of 0 would round every probability to 0 in fp16.  Left
     padding (first 130 keys) and an interior gap, all valid logits ~ -40."""
     L = _lib(); lib = L.load()
     B, T, H = 2, 400, 2
-    E = 64 * H
+    E = D * H
     g = torch.Generator(device="cpu").manual_seed(17)
-    u = torch.randn(64, generator=g)
+    u = torch.randn(D, generator=g)
     u = u / u.norm() * (40.0 ** 0.5)
     qkv = 0.05 * torch.randn(B * T, 3 * E, generator=g)
     for h in range(H):
-        qkv[:, h * 64:(h + 1) * 64] += u
-        qkv[:, E + h * 64:E + (h + 1) * 64] -= u
+        qkv[:, h * D:(h + 1) * D] += u
+        qkv[:, E + h * D:E + (h + 1) * D] -= u
     qkv[:, 2 * E:] = torch.randn(B * T, E, generator=g)
     qkv = qkv.half().to(dev)
     pad = torch.zeros(B, T, dtype=torch.uint8)
@@ -210,8 +244,9 @@ def test_attention_left_and_interior_padding_with_very_negative_scores(dev):
     ctx = torch.full((B * T, E), float("nan"), dtype=torch.float16, device=dev)
     probs = torch.full((B, H, T, T), float("nan"), device=dev)
     scratch = torch.empty(lib.esmb200_attention_scratch_bytes(B, T), dtype=torch.uint8, device=dev)
-    L.check(lib.esmb200_attention(P(qkv), P(pad), P(ctx), P(probs), B, T, H, P(scratch), S()))
-    ref_o, ref_p = _attention_ref(qkv, pad, B, T, H)
+    fn = lib.esmb200_attention if D == 64 else lib.esmb200_attention128
+    L.check(fn(P(qkv), P(pad), P(ctx), P(probs), B, T, H, P(scratch), S()))
+    ref_o, ref_p = _attention_ref(qkv, pad, B, T, H, D)
     assert float(ref_o.abs().max()) > 0.05
     torch.testing.assert_close(ctx.float(), ref_o, atol=4e-3, rtol=4e-3)
     torch.testing.assert_close(probs, ref_p, atol=2e-5, rtol=1e-3)
@@ -229,6 +264,39 @@ def test_embed_tokens(dev):
     tk = tokens.to(dev)
     L.check(lib.esmb200_embed_tokens(P(tk), P(tab), P(x), 3, 40, 128, 1, 32, 1, S()))
     torch.testing.assert_close(x.cpu(), ref, atol=1e-6, rtol=1e-6)
+
+
+def test_embed_tokens_row_chunks(dev):
+    """The row-chunked grid (several blocks per sequence) against the oracle on a longer ragged batch, with and without
+    token dropout; T is not a multiple of the chunk size."""
+    from oracle import esm2_oracle
+    from oracle.weights import make_state_dict, make_tokens
+    L = _lib(); lib = L.load()
+    sd = make_state_dict(1, 320, 20)
+    tokens = make_tokens([1001, 333, 20], 1003, n_mask=5)
+    tab = sd["embed_tokens.weight"].to(dev)
+    for dropout in (1, 0):
+        ref = esm2_oracle.embed(tokens, sd, bool(dropout))
+        x = torch.full((3, 1003, 320), float("nan"), device=dev)
+        L.check(lib.esmb200_embed_tokens(P(tokens.to(dev)), P(tab), P(x), 3, 1003, 320, 1, 32, dropout, S()))
+        torch.testing.assert_close(x.cpu(), ref, atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("B,T,E", [(3, 40, 128), (2, 1024, 1280), (5, 77, 320), (1, 2, 64)])
+def test_mean_pool(dev, B, T, E):
+    """scripts/extract.py:116-119: mean over the residues 1 .. len (the <cls> row excluded), lengths 1 .. T-1."""
+    L = _lib(); lib = L.load()
+    g = torch.Generator().manual_seed(B * 31 + T)
+    x = torch.randn(B, T, E, generator=g).to(dev)
+    lens = [T - 1] + [max(1, (T - 1) // (b + 2)) for b in range(B - 1)]
+    lengths = torch.tensor(lens, dtype=torch.int32, device=dev)
+    out = torch.full((B, E), float("nan"), device=dev)
+    L.check(lib.esmb200_mean_pool(P(x), P(lengths), P(out), B, T, E, S()))
+    ref = torch.stack([x[b, 1: 1 + n].double().mean(0) for b, n in enumerate(lens)]).float()
+    torch.testing.assert_close(out, ref, atol=2e-6, rtol=1e-5)
+    out2 = torch.empty_like(out)
+    L.check(lib.esmb200_mean_pool(P(x), P(lengths), P(out2), B, T, E, S()))
+    assert torch.equal(out, out2)
 
 
 def test_error_reporting(dev):

@@ -32,7 +32,7 @@ def build_model(L, E, H, seed=0):
     return model.eval().cuda(), sd
 
 
-@pytest.mark.parametrize("name", ["tiny_L2_E128_H2", "mid_L3_E256_H4", "nopad_L2_E128_H2"])
+@pytest.mark.parametrize("name", ["tiny_L2_E128_H2", "mid_L3_E256_H4", "nopad_L2_E128_H2", "t48_15B_like_L2_E256_H2"])
 def test_against_reference_golden(name, golden_dir):
     fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     cfg = fx["config"]

@@ -4,7 +4,7 @@
   configs[3]  esm2_t36_3B:   all 36 layers at T = 512, one sequence, attentions + contacts
   configs[4]  esm_msa1b:     all 12 layers on a padded 32 x 256 MSA
   configs[0]  esm2_t6_8M:    the committed output of the unmodified reference (head_dim 16, tests/golden)
-  head_dim 24 / 32 (35M / 150M widths), fp16 parameters (ESMFold's `esm.half()`), all-layer export.
+  head_dim 24 / 32 (35M / 150M widths), 96 / 128 (15B's width), fp16 parameters (ESMFold's `esm.half()`), all-layer export.
 
 Tolerances are the stated ones of DESIGN.md §4 — relative Frobenius AND max-abs (scaled by the reference's rms, the
 reference's own precedent is atol 1e-3 on embeddings of rms ~0.2: /root/reference/tests/test_readme.py:116).
@@ -174,6 +174,47 @@ def test_narrow_heads_vs_oracle(L, E, H):
     assert rel_fro(out["logits"].cpu(), ref["logits"]) <= REL_FRO_LOGITS
     assert float((out["attentions"].cpu() - ref["attentions"]).abs().max()) <= ATT_ABS
     assert float((out["contacts"].cpu() - ref["contacts"]).abs().max()) <= CONTACT_ABS
+
+
+@pytest.mark.parametrize("L,E,H", [(3, 256, 2), (2, 640, 5), (2, 192, 2)])
+def test_wide_heads_vs_oracle(L, E, H):
+    """head_dim 128 — esm2_t48_15B's head width (pretrained.py:390-397), at small widths — and 96: two 64-wide column
+    slots per head, 64-column rope tables; ragged batch with <mask> tokens, attentions and contacts (the separate
+    probability + accumulation kernels: the fused contact pass is a head_dim <= 64 kernel)."""
+    from oracle import esm2_oracle
+    from oracle.weights import make_tokens
+    model, sd = build_model(L, E, H)
+    tokens = make_tokens([150, 77, 9], 152, seed=8, n_mask=2)
+    ref = esm2_oracle.esm2_forward(sd, L, H, tokens, repr_layers=[0, 1, L], return_contacts=True)
+    out = model(tokens.cuda(), repr_layers=[0, 1, L], return_contacts=True)
+    for k in (0, 1, L):
+        r = rel_fro(out["representations"][k].cpu(), ref["representations"][k])
+        assert r <= REL_FRO, (k, r)
+    ra = float((out["attentions"].cpu() - ref["attentions"]).abs().max())
+    rc = float((out["contacts"].cpu() - ref["contacts"]).abs().max())
+    report(f"wide_heads_L{L}_E{E}_H{H}", repr=rel_fro(out["representations"][L].cpu(), ref["representations"][L]),
+           logits=rel_fro(out["logits"].cpu(), ref["logits"]), attn_abs=ra, contacts_abs=rc)
+    assert rel_fro(out["logits"].cpu(), ref["logits"]) <= REL_FRO_LOGITS
+    assert ra <= ATT_ABS and rc <= CONTACT_ABS
+    # embeddings only (no probabilities): the same representations bit for bit
+    out2 = model(tokens.cuda(), repr_layers=[L])
+    assert torch.equal(out2["representations"][L], out["representations"][L])
+    with pytest.raises(ValueError):
+        model.set_precision("fp32x3")
+
+
+def test_15B_layer_shape_runs():
+    """One layer at the real 15B shape (5120 wide, 40 heads of 128, FFN 20480) on 2 x 300 tokens vs the oracle."""
+    from oracle import esm2_oracle
+    from oracle.weights import make_tokens
+    model, sd = build_model(1, 5120, 40)
+    tokens = make_tokens([298, 123], 300, seed=9)
+    ref = esm2_oracle.esm2_forward(sd, 1, 40, tokens, repr_layers=[1], need_head_weights=True)
+    out = model(tokens.cuda(), repr_layers=[1], need_head_weights=True)
+    r = rel_fro(out["representations"][1].cpu(), ref["representations"][1])
+    ra = float((out["attentions"].cpu() - ref["attentions"]).abs().max())
+    report("esm2_15B_shape_1_layer", repr=r, attn_abs=ra)
+    assert r <= REL_FRO and ra <= ATT_ABS
 
 
 def test_half_model_all_layers_like_esmfold():

@@ -44,7 +44,8 @@ def _reference_model(esm, L, E, H, seed=0):
     return model.eval()
 
 
-@pytest.mark.parametrize("name", ["tiny_L2_E128_H2", "mid_L3_E256_H4", "t6_8M_like_L6_E320_H20"])
+@pytest.mark.parametrize("name", ["tiny_L2_E128_H2", "mid_L3_E256_H4", "t6_8M_like_L6_E320_H20",
+                                  "t48_15B_like_L2_E256_H2"])
 def test_reference_esm2_forward_on_the_library(esm_ref, name, golden_dir):
     from esm_b200 import _lib, integration
     fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
