@@ -118,10 +118,11 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* kv_full = bars + 2;    // [2] TMA -> MMA
   uint64_t* kv_empty = bars + 4;   // [2] MMA -> TMA (2 arrivals: K released by QK^T, V by P.V)
   uint64_t* s_full = bars + 6;     // [SBUF] MMA -> softmax: S_j written (DS 1: and P.V(j-1) accumulated)
-  uint64_t* p_full = bars + 8;     // [1] softmax -> MMA: P_j stored (128 arrivals)
-  uint64_t* o_full = bars + 9;     // [1] MMA -> softmax: last P.V of the tile accumulated
-  uint64_t* pv_done = bars + 10;   // [1] DS 2: one completion per P.V (reference-max raise); ESMB200_ATTN8_SAFE_WAR
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* p_full = bars + 8;     // [SBUF] softmax -> MMA: P_j stored (128 arrivals).  One per S buffer: with two buffers a
+                                   // fast warp is a block ahead of a slow one, and arrivals on ONE barrier are anonymous
+  uint64_t* o_full = bars + 10;    // [1] MMA -> softmax: last P.V of the tile accumulated
+  uint64_t* pv_done = bars + 11;   // [1] DS 2: one completion per P.V (reference-max raise); ESMB200_ATTN8_SAFE_WAR
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const uint32_t warp = threadIdx.x / 32;
   const uint32_t lane = threadIdx.x % 32;
@@ -139,7 +140,8 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 128);
+    mbar_init(&p_full[0], 128);
+    mbar_init(&p_full[1], 128);
     mbar_init(o_full, 1);
     mbar_init(pv_done, 1);
     fence_barrier_init();
@@ -232,10 +234,12 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         issue_qk(g, nblk == 1);
         for (int j = 0; j < nblk; ++j, ++g, ++np) {
           const uint32_t s = g % KV_STAGES;
+#ifndef ESMB200_ATTN8_DS2_LATE_QK
           if constexpr (DS == 2) {  // S_{j+1} is produced while the softmax warps work on S_j
             if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }
-          mbar_wait(p_full, np & 1);  // P_j stored (and, on the first block of a tile, the previous O read out)
+#endif
+          mbar_wait(&p_full[g % SBUF], (g / SBUF) & 1);  // P_j stored (first block of a tile: and the previous O read out)
           tc_fence_after();
           [[maybe_unused]] const uint32_t tmem_p = tmem_s + (g % SBUF) * 64;
           const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KB), 1024, 8192);
@@ -262,6 +266,11 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
             tc_commit(pv_done);
             mbar_wait(pv_done, np & 1);
             tc_fence_after();
+          }
+#endif
+#ifdef ESMB200_ATTN8_DS2_LATE_QK
+          if constexpr (DS == 2) {
+            if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }
 #endif
           if constexpr (DS == 2) {
@@ -391,7 +400,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full);
+        mbar_arrive(&p_full[sb]);
         l_run += rsum;
       }
 

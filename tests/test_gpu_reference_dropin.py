@@ -95,6 +95,34 @@ def test_patched_reference_equals_reference_eager_on_the_same_gpu(esm_ref):
     assert rel_fro(fast16[L].float()[keep], eager[keep]) <= 8e-3  # fp16 weights + fp16 reference prologue/tail
 
 
+def test_reference_650M_full_size_eager_vs_library(esm_ref):
+    """BASELINE.json configs[1] at full size with the REAL reference on both sides: the unmodified `ESM2` of fair-esm
+    (33 x 1280 x 20 heads) on the GPU in eager fp32 (TF32 off) against the same object with its TransformerLayer.forward
+    substituted, T = 1024, two sequences (one padded to 700 residues): last representation, logits, contacts."""
+    from esm_b200 import integration
+    from oracle.weights import make_tokens
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    L, E, H = 33, 1280, 20
+    model = _reference_model(esm_ref, L, E, H).cuda()
+    tokens = make_tokens([1022, 700], 1024, seed=4, n_mask=3).cuda()
+    with torch.no_grad():
+        eager = model(tokens, repr_layers=[L], return_contacts=True)
+        eager = {"rep": eager["representations"][L], "logits": eager["logits"], "contacts": eager["contacts"]}
+    integration.patch_reference(esm_ref.modules)
+    try:
+        with torch.no_grad():
+            fast = model(tokens, repr_layers=[L], return_contacts=True)
+    finally:
+        integration.unpatch_reference(esm_ref.modules)
+    keep = tokens.ne(1)
+    r = rel_fro(fast["representations"][L][keep], eager["rep"][keep])
+    rl = rel_fro(fast["logits"][keep], eager["logits"][keep])
+    rc = float((fast["contacts"] - eager["contacts"])[0].abs().max())  # sequence 0 has no padding
+    print(f"PARITY reference_eager_650M_T1024 repr={r:.3e} logits={rl:.3e} contacts_abs={rc:.3e}", flush=True)
+    assert r <= 3e-3 and rl <= 4e-3 and rc <= 1e-2
+
+
 def test_cpu_tensors_keep_the_reference_path(esm_ref):
     """Like the FusedLayerNorm precedent: on CPU the substituted class runs the reference's own PyTorch code."""
     from esm_b200 import integration
