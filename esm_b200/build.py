@@ -13,8 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libesmb200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "gemm_common.cuh", "gemm2.cuh", "attention_common.cuh", "attention_probs.cuh", "attention7.cuh",
-           "attention8.cuh", "tied_attention.cuh", "elementwise.cuh", os.path.join("..", "..", "include", "esmb200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "esmb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
