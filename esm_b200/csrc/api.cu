@@ -20,7 +20,6 @@
 
 #include "attention7.cuh"
 #include "attention8.cuh"
-#include "attention9.cuh"
 #include "attention_contact.cuh"
 #include "attention_probs.cuh"
 #include "common.cuh"
@@ -138,7 +137,7 @@ int g_attn_version = -1, g_attn_poly = -1;  // -1: take the environment / defaul
 int attn_version() {
   if (g_attn_version < 0) {
     const char* e = getenv("ESMB200_ATTN");
-    g_attn_version = (e && e[0] == '7') ? 7 : (e && e[0] == '9') ? 9 : 8;
+    g_attn_version = (e && e[0] == '7') ? 7 : 8;
   }
   return g_attn_version;
 }
@@ -156,12 +155,6 @@ cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, 
   if (ap.lo_off > 0) return launch_attention_v8_poly<0, true>(tq, tkv, ap, sms, st);  // fp32x3: all exponentials on MUFU
   if (ap.slots == 2) return launch_attention_v8_poly<4, false, 2>(tq, tkv, ap, sms, st);  // head_dim <= 128 (15B)
   if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
-  if (attn_version() == 9) {
-    switch (attn_poly()) {
-      case 0: return launch_attention_v9_poly<0>(tq, tkv, ap, sms, st);
-      default: return launch_attention_v9_poly<4>(tq, tkv, ap, sms, st);
-    }
-  }
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
     case 2: return launch_attention_v8_poly<2>(tq, tkv, ap, sms, st);
@@ -1138,7 +1131,7 @@ int esmb200_debug_read_attn_trace(long long* out, int32_t n) {
 
 int esmb200_set_option(const char* name, int32_t value) {
   if (!name) return fail(ESMB200_EINVAL, "null option name");
-  if (!strcmp(name, "attn") && (value == 7 || value == 8 || value == 9)) { g_attn_version = value; return ESMB200_OK; }
+  if (!strcmp(name, "attn") && (value == 7 || value == 8)) { g_attn_version = value; return ESMB200_OK; }
   if (!strcmp(name, "attn_poly") && (value == 0 || value == 2 || value == 3 || value == 4)) {
     g_attn_poly = value;
     return ESMB200_OK;

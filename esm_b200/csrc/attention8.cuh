@@ -54,7 +54,7 @@ constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 1024 + 128;
 // same fp32 accumulator.  Twice the shared memory per tile -> 2 CTAs per SM.
 constexpr int SMEM_BYTES_SPLIT = 2 * Q_BYTES + KV_STAGES * 4 * KV_BYTES + 1024 + 128;
 constexpr int CTAS_PER_SM_SPLIT = 2;
-constexpr int TMEM_COLS_WIDE = 256;    // DS = 2: S/P [0,64) | O [64,192)
+constexpr int TMEM_COLS_WIDE = 256;    // DS = 2: S0/P0 [0,64) | S1/P1 [64,128) | O [128,256)
 constexpr float SUM_LIMIT = 4096.0f;   // raise the reference when a block's row sum exceeds this
 }  // namespace attn8_cfg
 
@@ -124,7 +124,18 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* pv_done = bars + 11;   // [1] DS 2: one completion per P.V (reference-max raise); ESMB200_ATTN8_SAFE_WAR
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const uint32_t warp = threadIdx.x / 32;
+  // Roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = softmax (the four TMEM lane quarters need warps 2-5).
+  // Warps 0 and 1 sit on scheduler sub-partitions 0 and 1 in EVERY CTA; tcgen05 instructions of one sub-partition are
+  // dispatched one after the other (~80 cycles each, measured), so with the issuer always on warp 1 the four CTAs of an
+  // SM serialised their 11 instructions per block on one port.  CTAs of the second / fourth residency slot swap the two
+  // control warps (ESMB200_ATTN8_NO_ROLE_SWAP disables it for A/B).
+#ifdef ESMB200_ATTN8_NO_ROLE_SWAP
+  const uint32_t swap = 0;
+#else
+  const uint32_t swap = p.num_sms > 0 ? ((blockIdx.x / (uint32_t)p.num_sms) & 1u) : 0u;
+#endif
+  const uint32_t warp_phys = threadIdx.x / 32;
+  const uint32_t warp = warp_phys < 2 ? (warp_phys ^ swap) : warp_phys;
   const uint32_t lane = threadIdx.x % 32;
   const int nqt = (p.T + BLOCK_Q - 1) / BLOCK_Q;
   const int total = p.B * p.H * nqt;
@@ -482,7 +493,9 @@ inline cudaError_t launch_attention_v8_poly(const CUtensorMap& tmap_q, const CUt
   const long long total = (long long)p.B * p.H * ((p.T + BLOCK_Q - 1) / BLOCK_Q);
   const long long cap = (long long)(two ? CTAS_PER_SM_SPLIT : CTAS_PER_SM) * num_sms;
   const int grid = (int)(total < cap ? total : cap);
-  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, p);
+  AttnParams pp = p;
+  pp.num_sms = num_sms;
+  return launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, tmap_q, tmap_kv, pp);
 }
 
 }  // namespace esmb200

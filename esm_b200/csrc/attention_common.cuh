@@ -19,6 +19,8 @@ struct AttnParams {
   float* row_max;           // optional [B,H,T]: final softmax row max (of the scaled scores) ...
   float* row_sum;           // optional [B,H,T]: ... and row sum of exp(s - max), for attention_probs_kernel
   int lo_off = 0;           // fp32x3 precision: column offset (elements) of the lo halves in qkv [M, 6E] (= 3E)
+  int num_sms = 0;          // SMs of the device (set by the launcher): CTA b is assumed to sit on SM b % num_sms, used only to
+                            // spread the MMA-issuing warps of co-resident CTAs over two scheduler sub-partitions
   int slots = 1;            // 64-wide column slots per head: 1 (head_dim <= 64) or 2 (head_dim <= 128); E = H * 64 * slots
   int cols = 1;             // sequence s = (s / cols, s % cols) of a [B/cols, T, cols, 3E] tensor
                             // (MSA column attention: the T tokens of a sequence are `cols` rows apart)
