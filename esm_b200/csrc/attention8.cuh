@@ -116,7 +116,8 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint64_t* q_full = bars;         // [1] TMA -> MMA
   uint64_t* q_empty = bars + 1;    // [1] MMA -> TMA (every QK^T of the tile has completed)
   uint64_t* kv_full = bars + 2;    // [2] TMA -> MMA
-  uint64_t* kv_empty = bars + 4;   // [2] MMA -> TMA (2 arrivals: K released by QK^T, V by P.V)
+  uint64_t* kv_empty = bars + 4;   // [2] MMA -> TMA: the commit behind P.V(j) releases K_j and V_j together (every tcgen05
+                                   // instruction of the issuing thread costs ~94 cycles of the per-block chain: one commit less)
   uint64_t* s_full = bars + 6;     // [SBUF] MMA -> softmax: S_j written (DS 1: and P.V(j-1) accumulated)
   uint64_t* p_full = bars + 8;     // [SBUF] softmax -> MMA: P_j stored (128 arrivals).  One per S buffer: with two buffers a
                                    // fast warp is a block ahead of a slow one, and arrivals on ONE barrier are anonymous
@@ -134,7 +135,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
 #else
   const uint32_t swap = p.num_sms > 0 ? ((blockIdx.x / (uint32_t)p.num_sms) & 1u) : 0u;
 #endif
-  const uint32_t warp_phys = threadIdx.x / 32;
+  const uint32_t warp_phys = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);  // warp-uniform for the compiler
   const uint32_t warp = warp_phys < 2 ? (warp_phys ^ swap) : warp_phys;
   const uint32_t lane = threadIdx.x % 32;
   const int nqt = (p.T + BLOCK_Q - 1) / BLOCK_Q;
@@ -147,7 +148,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
     mbar_init(q_empty, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);
+      mbar_init(&kv_empty[i], 1);
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
@@ -207,39 +208,55 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: QK^T(0), then [P.V(j); QK^T(j+1)] per block =====================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop and only the tcgen05 instructions sit under elect_one(): with every operand derived
+    // from warp-uniform values (shuffles of lane 0, kernel parameters, loop counters) ptxas keeps descriptors and TMEM
+    // addresses in uniform registers and emits the eight UTCHMMA of a block back to back.  The round-1 form — `if
+    // (lane == 0)` around the loop — made every operand "divergent": each tcgen05.mma was wrapped in an ELECT / 2x
+    // R2UR.BROADCAST / BRA.U.ANY waterfall, ~94 cycles per instruction on the per-block critical chain (clock64 trace,
+    // scripts/attn_trace8.py).
+    {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 64, false);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, true);
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(smem_q), 1024, 0);
-      const uint64_t qdesc_lo = umma_smem_desc_sw128(smem_u32(smem_q + Q_BYTES), 1024, 0);  // SPLIT: lo; DS 2: slot 1
+      const uint32_t u_smem = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t u_q = u_smem, u_k = u_smem + QB, u_v = u_smem + QB + KV_STAGES * KB;
+      const uint32_t u_bars = u_smem + QB + KV_STAGES * 2 * KB;  // byte address of bars[0]
+      const uint32_t u_tmem_s = __shfl_sync(0xffffffffu, tmem_s, 0);
+      const uint32_t u_tmem_o = u_tmem_s + 64 * SBUF;
+      auto bar_addr = [&](const uint64_t* b) -> uint32_t { return u_bars + (uint32_t)(b - bars) * 8u; };
+      const uint64_t qdesc = umma_smem_desc_sw128(u_q, 1024, 0);
+      const uint64_t qdesc_lo = umma_smem_desc_sw128(u_q + Q_BYTES, 1024, 0);  // SPLIT: lo; DS 2: slot 1
       uint32_t g = 0, tq = 0, np = 0;
       auto issue_qk = [&](uint32_t gg, bool last) {
         const uint32_t s = gg % KV_STAGES;
         mbar_wait(&kv_full[s], (gg / KV_STAGES) & 1);
         tc_fence_after();
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem_k + s * KB), 1024, 0);
+        ATRACE(3, gg);
+        const uint64_t kdesc = umma_smem_desc_sw128(u_k + s * KB, 1024, 0);
         const uint32_t sb = gg % SBUF;
-        const uint32_t tmem_sb = tmem_s + sb * 64;
+        const uint32_t tmem_sb = u_tmem_s + sb * 64;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-        if constexpr (SPLIT) {  // + q_lo k_hi + q_hi k_lo
-          const uint64_t kdesc_lo = umma_smem_desc_sw128(smem_u32(smem_k + s * KB + KV_BYTES), 1024, 0);
+          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          if constexpr (SPLIT) {  // + q_lo k_hi + q_hi k_lo
+            const uint64_t kdesc_lo = umma_smem_desc_sw128(u_k + s * KB + KV_BYTES, 1024, 0);
 #pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc_lo + 2 * k, kdesc + 2 * k, idesc_qk, 1u);
+            for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(u_tmem_s, qdesc_lo + 2 * k, kdesc + 2 * k, idesc_qk, 1u);
 #pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_s, qdesc + 2 * k, kdesc_lo + 2 * k, idesc_qk, 1u);
+            for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(u_tmem_s, qdesc + 2 * k, kdesc_lo + 2 * k, idesc_qk, 1u);
+          }
+          if constexpr (DS == 2) {  // + q[slot 1] . k[slot 1]
+            const uint64_t kdesc1 = umma_smem_desc_sw128(u_k + s * KB + KV_BYTES, 1024, 0);
+#pragma unroll
+            for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc_lo + 2 * k, kdesc1 + 2 * k, idesc_qk, 1u);
+          }
+          tc_commit_addr(bar_addr(&s_full[sb]));
+          if (last) tc_commit_addr(bar_addr(q_empty));  // every QK^T of this tile issued: Q may be reloaded when they finish
         }
-        if constexpr (DS == 2) {  // + q[slot 1] . k[slot 1]
-          const uint64_t kdesc1 = umma_smem_desc_sw128(smem_u32(smem_k + s * KB + KV_BYTES), 1024, 0);
-#pragma unroll
-          for (int k = 0; k < HEAD_DIM / 16; ++k) umma_ss(tmem_sb, qdesc_lo + 2 * k, kdesc1 + 2 * k, idesc_qk, 1u);
-        }
-        tc_commit(&s_full[sb]);
-        tc_commit(&kv_empty[s]);
-        if (last) tc_commit(q_empty);  // every QK^T of this tile has been issued: Q may be reloaded when they finish
+        __syncwarp();
+        ATRACE(4, gg);
       };
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int nblk = n_blocks(w);
+        const int nblk = __shfl_sync(0xffffffffu, n_blocks(w), 0);
         if (nblk == 0) continue;
         mbar_wait(q_full, tq & 1);
         issue_qk(g, nblk == 1);
@@ -250,31 +267,45 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }
 #endif
-          mbar_wait(&p_full[g % SBUF], (g / SBUF) & 1);  // P_j stored (first block of a tile: and the previous O read out)
-          tc_fence_after();
-          [[maybe_unused]] const uint32_t tmem_p = tmem_s + (g % SBUF) * 64;
-          const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(smem_v + s * KB), 1024, 8192);
-#pragma unroll
-          for (int k = 0; k < BLOCK_KV / 16; ++k)
-            umma_ts(tmem_o, tmem_p + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
-          if constexpr (SPLIT) {  // + p_lo v_hi + p_hi v_lo (P_lo lives in columns [32,64) of the S buffer)
-            const uint64_t vdesc_lo = umma_smem_desc_sw128(smem_u32(smem_v + s * KB + KV_BYTES), 1024, 8192);
-#pragma unroll
-            for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(tmem_o, tmem_s + 32 + 8 * k, vdesc + 128 * k, idesc_pv, 1u);
-#pragma unroll
-            for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(tmem_o, tmem_s + 8 * k, vdesc_lo + 128 * k, idesc_pv, 1u);
+          ATRACE(0, g);
+          if constexpr (DS == 1) {  // K/V of the next block: wait now, while the softmax warps are still busy with block j
+            if (j + 1 < nblk) mbar_wait(&kv_full[(g + 1) % KV_STAGES], ((g + 1) / KV_STAGES) & 1);
           }
-          if constexpr (DS == 2) {  // O[:, 64:128] += P . v[slot 1]
-            const uint64_t vdesc1 = umma_smem_desc_sw128(smem_u32(smem_v + s * KB + KV_BYTES), 1024, 8192);
+          mbar_wait_spin(&p_full[g % SBUF], (g / SBUF) & 1);  // P_j stored (first block of a tile: and the previous O read out)
+          tc_fence_after();
+          ATRACE(1, g);
+          const uint32_t tmem_p = u_tmem_s + (g % SBUF) * 64;
+          const uint64_t vdesc = umma_smem_desc_sw128(u_v + s * KB, 1024, 8192);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_KV / 16; ++k)
-              umma_ts(tmem_o + 64, tmem_p + 8 * k, vdesc1 + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+              umma_ts(u_tmem_o, tmem_p + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            if constexpr (SPLIT) {  // + p_lo v_hi + p_hi v_lo (P_lo lives in columns [32,64) of the S buffer)
+              const uint64_t vdesc_lo = umma_smem_desc_sw128(u_v + s * KB + KV_BYTES, 1024, 8192);
+#pragma unroll
+              for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(u_tmem_o, u_tmem_s + 32 + 8 * k, vdesc + 128 * k, idesc_pv, 1u);
+#pragma unroll
+              for (int k = 0; k < BLOCK_KV / 16; ++k) umma_ts(u_tmem_o, u_tmem_s + 8 * k, vdesc_lo + 128 * k, idesc_pv, 1u);
+            }
+            if constexpr (DS == 2) {  // O[:, 64:128] += P . v[slot 1]
+              const uint64_t vdesc1 = umma_smem_desc_sw128(u_v + s * KB + KV_BYTES, 1024, 8192);
+#pragma unroll
+              for (int k = 0; k < BLOCK_KV / 16; ++k)
+                umma_ts(u_tmem_o + 64, tmem_p + 8 * k, vdesc1 + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+            tc_commit_addr(bar_addr(&kv_empty[s]));
+            if constexpr (DS == 2) tc_commit_addr(bar_addr(pv_done));
+#ifdef ESMB200_ATTN8_SAFE_WAR
+            if constexpr (DS == 1) tc_commit_addr(bar_addr(pv_done));
+#endif
+            if constexpr (DS == 2) {
+              if (j + 1 == nblk) tc_commit_addr(bar_addr(o_full));
+            }
           }
-          tc_commit(&kv_empty[s]);
-          if constexpr (DS == 2) tc_commit(pv_done);
+          __syncwarp();
+          ATRACE(2, g);
 #ifdef ESMB200_ATTN8_SAFE_WAR
           if constexpr (DS == 1) {
-            tc_commit(pv_done);
             mbar_wait(pv_done, np & 1);
             tc_fence_after();
           }
@@ -284,11 +315,13 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }
 #endif
-          if constexpr (DS == 2) {
-            if (j + 1 == nblk) tc_commit(o_full);
-          } else {
-            if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
-            else tc_commit(o_full);
+          if constexpr (DS == 1) {
+            if (j + 1 < nblk) {
+              issue_qk(g + 1, j + 2 == nblk);
+            } else {
+              if (elect_one()) tc_commit_addr(bar_addr(o_full));
+              __syncwarp();
+            }
           }
         }
         ++tq;
@@ -315,8 +348,10 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const uint32_t kw[2] = {kw2.x, kw2.y};
         const uint32_t sb = ns % SBUF;
         const uint32_t ts = ts0 + sb * 64;
+        if (threadIdx.x == 64) ATRACE(5, ns);
         mbar_wait(&s_full[sb], (ns / SBUF) & 1);
         tc_fence_after();
+        if (threadIdx.x == 64) ATRACE(6, ns);
         if (!seeded) {  // uniform over the CTA: the key mask is per sequence
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -403,6 +438,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
           m_ref = m_new;
         }
         // P_j over the first 32 columns of S_j (this thread's own row, already consumed)
+        if (threadIdx.x == 64) ATRACE(8, ns);
         tmem_st_32x32b_x16(ts, pk[0]);
         tmem_st_32x32b_x16(ts + 16, pk[1]);
         if constexpr (SPLIT) {
@@ -412,6 +448,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&p_full[sb]);
+        if (threadIdx.x == 64) ATRACE(9, ns);
         l_run += rsum;
       }
 

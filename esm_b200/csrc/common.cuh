@@ -106,6 +106,38 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
+// Spinning wait for a thread that sits on a kernel's critical path (the MMA issuer waiting for P): test_wait returns at
+// once, so the thread notices the phase flip a few cycles after the last arrival instead of after try_wait's
+// suspend / resume round trip (~200 cycles measured in the attention kernel).  One thread only: it burns issue slots.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#if ESMB200_WATCHDOG
+  uint32_t polls = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++polls == (1u << 28)) {
+      printf("esmb200: mbarrier watchdog (spin) block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#else
+  while (!mbar_test_wait(bar, parity)) {
+  }
+#endif
+}
+
 // Wait used by producer threads that run far ahead of their consumers (TMA rings): back off between polls so the
 // polling thread does not take issue slots from the compute warps sharing its SM sub-partition.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
@@ -186,6 +218,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// the same with the barrier's shared-memory byte address (lets the caller keep it in a uniform register)
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_smem_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers fp16 and bf16 operands with fp32 accumulation
@@ -353,6 +390,13 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask)
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_addr(uint32_t bar_smem_addr, uint16_t cta_mask) {  // uniform-register form
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar_smem_addr),
       "h"(cta_mask)
       : "memory");
 }

@@ -73,7 +73,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES] used in the leader CTA only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
 
-  const uint32_t warp = threadIdx.x / 32;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0);  // warp-uniform for the compiler
   const uint32_t lane = threadIdx.x % 32;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -153,26 +153,38 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane of the leader CTA) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA): the whole warp runs the loop, one elected lane issues =====================
+    // Convergent control flow + operands derived from warp-uniform values keep descriptors, TMEM addresses and barrier
+    // addresses in uniform registers, so the four UTCHMMA of a K slab and the commit are issued back to back.  With
+    // `if (lane == 0)` around the loop ptxas wrapped every tcgen05 instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // waterfall (~94 cycles each, measured in the attention kernel): 5 x 94 per slab against 512 cycles of tensor work.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_f16(PAIR_M, BLOCK_N, false);
+      const uint32_t u_smem = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t u_a = u_smem, u_b = u_smem + STAGES * A_STAGE_BYTES;
+      const uint32_t u_bars = u_smem + STAGES * STAGE_BYTES + NUM_STG * STG_BYTES;
+      const uint32_t u_empty = u_bars + STAGES * 8, u_tfull = u_bars + 2 * STAGES * 8;
+      const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t stage = 0, phase = 0;
       int iter = 0;
       for (int tile = tile_first; iter < tile_count; tile += tile_step, ++iter) {
         const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = u_tmem + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES), 1024, 0);
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * B_STAGE_BYTES), 1024, 0);
+          const uint64_t adesc = umma_smem_desc_sw128(u_a + stage * A_STAGE_BYTES, 1024, 0);
+          const uint64_t bdesc = umma_smem_desc_sw128(u_b + stage * B_STAGE_BYTES, 1024, 0);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_pair(&empty_bar[stage], 0b11);
-          if (kb == num_kb - 1) tc_commit_pair(&tfull_bar[as], 0b11);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_pair_addr(u_empty + stage * 8, 0b11);
+            if (kb == num_kb - 1) tc_commit_pair_addr(u_tfull + as * 8, 0b11);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
