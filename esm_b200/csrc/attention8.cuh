@@ -27,10 +27,11 @@
 // DS = 2 (64 < head_dim <= 128, ESM-2 15B): a head is TWO 64-wide slots (elementwise.cuh head_slot).  QK^T accumulates
 // both slots into the same S (8 MMAs), P.V runs once per slot into two 64-column halves of O: 256 TMEM columns, twice
 // the shared memory -> 2 CTAs per SM.  Two CTAs do not hide the serial per-CTA chain (first version: 400 TF/s), and
-// 256 columns leave room for a second S buffer: S0 [0,64) | S1 [64,128) | O [128,256).  QK^T(j+1) is issued BEFORE the
-// wait for P_j, so the tensor core fills S_{j+1} while the softmax warps work on S_j.  The "S_{j+1} ready => P.V(j)
-// accumulated" property of the single-buffer pipeline is gone, so the rare reference-max raise waits on pv_done (one
-// commit per P.V) before it rescales O.
+// 256 columns leave room for a second S buffer: S0 [0,64) | S1 [64,128) | O [128,256), so P_j and S_{j+1} do not share
+// columns.  Issuing QK^T(j+1) BEFORE the wait for P_j (ESMB200_ATTN8_DS2_EARLY_QK) would let the tensor core fill S_{j+1}
+// under the softmax of block j, but with two 32 KB K/V stages per CTA the K/V of block j+1 is then still in flight
+// (clock64 trace: 1640 cycles of the 2730-cycle block spent on kv_full) — the default keeps the d = 64 order
+// [P.V(j); QK^T(j+1)].  Either way the rare reference-max raise waits on pv_done (one commit per P.V) before it rescales O.
 // (A 3-CTA/SM build — 96 registers, both 32-column S loads of a block in flight behind one wait — measured slower:
 // 2.32-2.47 ms vs 2.04-2.06 ms at B = 256, profiles/r02_attention_sweep.txt: occupancy beats per-warp load depth.)
 #pragma once
@@ -262,15 +263,16 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
         issue_qk(g, nblk == 1);
         for (int j = 0; j < nblk; ++j, ++g, ++np) {
           const uint32_t s = g % KV_STAGES;
-#ifndef ESMB200_ATTN8_DS2_LATE_QK
+#ifdef ESMB200_ATTN8_DS2_EARLY_QK
           if constexpr (DS == 2) {  // S_{j+1} is produced while the softmax warps work on S_j
             if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }
 #endif
           ATRACE(0, g);
-          if constexpr (DS == 1) {  // K/V of the next block: wait now, while the softmax warps are still busy with block j
-            if (j + 1 < nblk) mbar_wait(&kv_full[(g + 1) % KV_STAGES], ((g + 1) / KV_STAGES) & 1);
-          }
+#ifndef ESMB200_ATTN8_DS2_EARLY_QK
+          // K/V of the next block: wait now, while the softmax warps are still busy with block j
+          if (j + 1 < nblk) mbar_wait(&kv_full[(g + 1) % KV_STAGES], ((g + 1) / KV_STAGES) & 1);
+#endif
           mbar_wait_spin(&p_full[g % SBUF], (g / SBUF) & 1);  // P_j stored (first block of a tile: and the previous O read out)
           tc_fence_after();
           ATRACE(1, g);
@@ -310,7 +312,7 @@ attention_fwd_kernel_v8(const __grid_constant__ CUtensorMap tmap_q, const __grid
             tc_fence_after();
           }
 #endif
-#ifdef ESMB200_ATTN8_DS2_LATE_QK
+#ifndef ESMB200_ATTN8_DS2_EARLY_QK
           if constexpr (DS == 2) {
             if (j + 1 < nblk) issue_qk(g + 1, j + 2 == nblk);
           }

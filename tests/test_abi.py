@@ -80,3 +80,34 @@ def test_state_dict_keys_match_reference_layout():
     assert set(model.state_dict().keys()) == set(sd.keys())
     model.load_state_dict(sd, strict=True)
     assert model.lm_head.weight is model.embed_tokens.weight
+
+
+def test_mma_issuer_sass_has_no_waterfall_loops():
+    """The tcgen05.mma issue loops are warp-convergent with uniform operands: in the SASS of the shipped
+    library the UTCHMMA of the attention and GEMM kernels must not sit in ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall
+    loops (one per instruction in the round-1 form: ~94 cycles each on the attention kernel's critical chain).  The few
+    remaining BRA.U.ANY belong to the single-lane TMA load / store issuers."""
+    import shutil
+    import subprocess
+    from esm_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    counts, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            counts[cur] = {"UTCHMMA": 0, "BRA.U.ANY": 0}
+        elif cur:
+            if "UTCHMMA" in line:
+                counts[cur]["UTCHMMA"] += 1
+            if "BRA.U.ANY" in line:
+                counts[cur]["BRA.U.ANY"] += 1
+    checked = 0
+    for name, c in counts.items():
+        if ("attention_fwd_kernel_v8" in name or "gemm2_f16_kernel" in name) and c["UTCHMMA"] > 0:
+            checked += 1
+            # round-1 form: one waterfall per UTCHMMA and per commit on top of these (GEMM: 12, attention v8: 18+)
+            assert c["BRA.U.ANY"] <= 6, (name, c)
+    assert checked >= 10
