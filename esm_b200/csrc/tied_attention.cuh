@@ -64,7 +64,7 @@ tied_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* done = bars + 2 * S_STAGES;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S_STAGES + 1);
 
-  const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;  // warp: uniform for ptxas
   const int m0 = blockIdx.x * S_BM, n0 = blockIdx.y * S_BN;
   const int b = blockIdx.z / p.H, h = blockIdx.z % p.H;
 
@@ -91,32 +91,40 @@ tied_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   pdl_wait();
   const uint32_t tmem_d = *tmem_slot;
 
+  // Both control warps run their loops warp-convergent with operands derived from warp-uniform values; only the TMA /
+  // tcgen05 instructions sit under elect_one() (no per-instruction ELECT / R2UR / BRA.U.ANY waterfall: the R-deep loop of
+  // this kernel was issue-bound, 5 x ~94 cycles per alignment row against 256 cycles of tensor work).
+  const uint32_t u_smem = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+  const uint32_t u_bars = u_smem + S_STAGES * S_STAGE_BYTES;
   if (warp == 0) {
-    if (lane == 0) {
-      for (int r = 0; r < p.R; ++r) {
-        const uint32_t s = r % S_STAGES;
-        mbar_wait_relaxed(&empty[s], ((r / S_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], S_STAGE_BYTES);
-        const int row = (b * p.R + r) * p.C;
-        uint8_t* st = smem + s * S_STAGE_BYTES;
-        tma_load_2d(st, &tmap_q, &full[s], h * 64, row + m0);
-        tma_load_2d(st + S_A_BYTES, &tmap_k, &full[s], p.E + h * 64, row + n0);
+    for (int r = 0; r < p.R; ++r) {
+      const uint32_t s = r % S_STAGES;
+      mbar_wait_relaxed(&empty[s], ((r / S_STAGES) & 1) ^ 1);
+      const int row = (b * p.R + r) * p.C;
+      const uint32_t st = u_smem + s * S_STAGE_BYTES, fb = u_bars + s * 8;
+      if (elect_one()) {
+        mbar_arrive_expect_tx_addr(fb, S_STAGE_BYTES);
+        tma_load_2d_addr(st, &tmap_q, fb, h * 64, row + m0);
+        tma_load_2d_addr(st + S_A_BYTES, &tmap_k, fb, p.E + h * 64, row + n0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(S_BM, S_BN, false);
-      for (int r = 0; r < p.R; ++r) {
-        const uint32_t s = r % S_STAGES;
-        mbar_wait(&full[s], (r / S_STAGES) & 1);
-        tc_fence_after();
-        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem + s * S_STAGE_BYTES), 1024, 0);
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem + s * S_STAGE_BYTES + S_A_BYTES), 1024, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(S_BM, S_BN, false);
+    const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_d, 0);
+    for (int r = 0; r < p.R; ++r) {
+      const uint32_t s = r % S_STAGES;
+      mbar_wait(&full[s], (r / S_STAGES) & 1);
+      tc_fence_after();
+      const uint64_t adesc = umma_smem_desc_sw128(u_smem + s * S_STAGE_BYTES, 1024, 0);
+      const uint64_t bdesc = umma_smem_desc_sw128(u_smem + s * S_STAGE_BYTES + S_A_BYTES, 1024, 0);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (r | k) != 0 ? 1u : 0u);
-        tc_commit(&empty[s]);
+        for (int k = 0; k < 4; ++k) umma_ss(u_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (r | k) != 0 ? 1u : 0u);
+        tc_commit_addr(u_bars + (S_STAGES + s) * 8);
+        if (r + 1 == p.R) tc_commit_addr(u_bars + 2 * S_STAGES * 8);
       }
-      tc_commit(done);
+      __syncwarp();
     }
   } else {
     const uint32_t quarter = warp % 4;
@@ -221,7 +229,7 @@ tied_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
   uint64_t* done = bars + 2 * V_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V_STAGES + 1);
 
-  const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;  // warp: uniform for ptxas
   const int m0 = blockIdx.x * V_BM;
   const int r0 = blockIdx.y * V_ROWS;
   const int nr = min(V_ROWS, p.R - r0);
@@ -251,37 +259,43 @@ tied_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant
   pdl_wait();
   const uint32_t tmem_d = *tmem_slot;
 
+  // warp-convergent control warps, see tied_scores_kernel (16 MMAs per 64-key slab were 16 waterfalls here)
+  const uint32_t u_smem = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+  const uint32_t u_bars = u_smem + (uint32_t)(reinterpret_cast<uint8_t*>(bars) - smem);
   if (warp == 0) {
-    if (lane == 0) {
-      for (int j = 0; j < nk; ++j) {
-        const uint32_t s = j % V_STAGES;
-        mbar_wait_relaxed(&empty[s], ((j / V_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], V_P_BYTES + nr * V_V_BYTES);
-        uint8_t* st = smem + s * V_STAGE_BYTES;
-        tma_load_2d(st, &tmap_p, &full[s], j * 64, (h * p.B + b) * p.C + m0);
+    for (int j = 0; j < nk; ++j) {
+      const uint32_t s = j % V_STAGES;
+      mbar_wait_relaxed(&empty[s], ((j / V_STAGES) & 1) ^ 1);
+      const uint32_t st = u_smem + s * V_STAGE_BYTES, fb = u_bars + s * 8;
+      if (elect_one()) {
+        mbar_arrive_expect_tx_addr(fb, V_P_BYTES + nr * V_V_BYTES);
+        tma_load_2d_addr(st, &tmap_p, fb, j * 64, (h * p.B + b) * p.C + m0);
         for (int i = 0; i < nr; ++i)
-          tma_load_2d(st + V_P_BYTES + i * V_V_BYTES, &tmap_v, &full[s], 2 * p.E + h * 64,
-                      (b * p.R + r0 + i) * p.C + j * 64);
+          tma_load_2d_addr(st + V_P_BYTES + i * V_V_BYTES, &tmap_v, fb, 2 * p.E + h * 64,
+                           (b * p.R + r0 + i) * p.C + j * 64);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(V_BM, 64, true);
-      for (int j = 0; j < nk; ++j) {
-        const uint32_t s = j % V_STAGES;
-        mbar_wait(&full[s], (j / V_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + s * V_STAGE_BYTES);
-        const uint64_t pdesc = umma_smem_desc_sw128(base, 1024, 0);
+    constexpr uint32_t idesc = umma_idesc_f16(V_BM, 64, true);
+    const uint32_t u_tmem = __shfl_sync(0xffffffffu, tmem_d, 0);
+    for (int j = 0; j < nk; ++j) {
+      const uint32_t s = j % V_STAGES;
+      mbar_wait(&full[s], (j / V_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t base = u_smem + s * V_STAGE_BYTES;
+      const uint64_t pdesc = umma_smem_desc_sw128(base, 1024, 0);
+      if (elect_one()) {
         for (int i = 0; i < nr; ++i) {
           const uint64_t vdesc = umma_smem_desc_sw128(base + V_P_BYTES + i * V_V_BYTES, 1024, 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ss(tmem_d + 64 * i, pdesc + 2 * k, vdesc + 128 * k, idesc, (j | k) != 0 ? 1u : 0u);
+            umma_ss(u_tmem + 64 * i, pdesc + 2 * k, vdesc + 128 * k, idesc, (j | k) != 0 ? 1u : 0u);
         }
-        tc_commit(&empty[s]);
+        tc_commit_addr(u_bars + (V_STAGES + s) * 8);
+        if (j + 1 == nk) tc_commit_addr(u_bars + 2 * V_STAGES * 8);
       }
-      tc_commit(done);
+      __syncwarp();
     }
   } else {
     const uint32_t quarter = warp % 4;
