@@ -18,6 +18,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+    "smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed",
+    "smsp__mem_tensor_reads_op_utcmma_matrix_c.sum.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__warps_eligible.avg.per_cycle_active",
 ]
 
 
