@@ -106,38 +106,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
-// Spinning wait for a thread that sits on a kernel's critical path (the MMA issuer waiting for P): test_wait returns at
-// once, so the thread notices the phase flip a few cycles after the last arrival instead of after try_wait's
-// suspend / resume round trip (~200 cycles measured in the attention kernel).  One thread only: it burns issue slots.
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-#if ESMB200_WATCHDOG
-  uint32_t polls = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    if (++polls == (1u << 28)) {
-      printf("esmb200: mbarrier watchdog (spin) block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
-  }
-#else
-  while (!mbar_test_wait(bar, parity)) {
-  }
-#endif
-}
-
 // Wait used by producer threads that run far ahead of their consumers (TMA rings): back off between polls so the
 // polling thread does not take issue slots from the compute warps sharing its SM sub-partition.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
