@@ -18,7 +18,9 @@
 
 #include <mutex>
 
-#include "attention7.cuh"
+#ifdef ESMB200_EXPERIMENTS
+#include "attention7.cuh"  // round-1 kernel, A/B only
+#endif
 #include "attention8.cuh"
 #include "attention_contact.cuh"
 #include "attention_probs.cuh"
@@ -137,7 +139,11 @@ int g_attn_version = -1, g_attn_poly = -1;  // -1: take the environment / defaul
 int attn_version() {
   if (g_attn_version < 0) {
     const char* e = getenv("ESMB200_ATTN");
+#ifdef ESMB200_EXPERIMENTS
     g_attn_version = (e && e[0] == '7') ? 7 : 8;
+#else
+    g_attn_version = 8;
+#endif
   }
   return g_attn_version;
 }
@@ -154,7 +160,9 @@ cudaError_t launch_attention_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, 
                                  cudaStream_t st) {
   if (ap.lo_off > 0) return launch_attention_v8_poly<0, true>(tq, tkv, ap, sms, st);  // fp32x3: all exponentials on MUFU
   if (ap.slots == 2) return launch_attention_v8_poly<4, false, 2>(tq, tkv, ap, sms, st);  // head_dim <= 128 (15B)
+#ifdef ESMB200_EXPERIMENTS
   if (attn_version() == 7) return launch_attention_v7(tq, tkv, ap, sms, st);
+#endif
   switch (attn_poly()) {
     case 0: return launch_attention_v8_poly<0>(tq, tkv, ap, sms, st);
     case 2: return launch_attention_v8_poly<2>(tq, tkv, ap, sms, st);
@@ -1131,7 +1139,11 @@ int esmb200_debug_read_attn_trace(long long* out, int32_t n) {
 
 int esmb200_set_option(const char* name, int32_t value) {
   if (!name) return fail(ESMB200_EINVAL, "null option name");
+#ifdef ESMB200_EXPERIMENTS
   if (!strcmp(name, "attn") && (value == 7 || value == 8)) { g_attn_version = value; return ESMB200_OK; }
+#else
+  if (!strcmp(name, "attn") && value == 8) { g_attn_version = value; return ESMB200_OK; }
+#endif
   if (!strcmp(name, "attn_poly") && (value == 0 || value == 2 || value == 3 || value == 4)) {
     g_attn_poly = value;
     return ESMB200_OK;

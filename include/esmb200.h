@@ -257,7 +257,8 @@ int esmb200_attention_split(const void* qkv, const uint8_t* pad_mask, void* ctx,
                             int32_t H, void* scratch, void* stream);
 
 /* ---- process-wide kernel selection knobs (A/B measurements; the defaults are the product configuration) ----
- * "attn"      8 (default: attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, 2 CTAs/SM)          env ESMB200_ATTN
+ * "attn"      8 (attention8.cuh, 4 CTAs/SM) | 7 (attention7.cuh, the round-1 kernel: only in a library built with
+ *             -DESMB200_EXPERIMENTS, A/B measurements)                                          env ESMB200_ATTN
  * "attn_poly" 0 | 2 | 3 | 4 (default): every n-th pair of softmax exponentials on the FMA pipe   env ESMB200_ATTN_POLY
  * "pdl"       0 (default) | 1: programmatic dependent launch between the layer's kernels        env ESMB200_PDL
  * Returns ESMB200_EINVAL for an unknown name or value. Not thread-safe against concurrent launches. */
